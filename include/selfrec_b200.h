@@ -1,0 +1,345 @@
+/*
+ * selfrec_b200 -- C ABI of the B200-native hot path behind SELFRec's plugin surface.
+ *
+ * Every entry point takes plain pointers and sizes (no torch types).  Device pointers
+ * are raw CUDA addresses (e.g. tensor.data_ptr()); `stream` is a cudaStream_t passed as
+ * void* (NULL = legacy default stream).  All kernels are stream-ordered, never
+ * synchronise the device, and are CUDA-graph capturable.  Every function returns
+ * SRB_OK (0) or a negative error code; srb_last_error() gives the message.  There is
+ * no CPU fallback: device entry points fail with SRB_ERR_CUDA when no GPU is present.
+ *
+ * The reference (Coder-Yu/SELFRec) has no FFI; each entry point names the reference
+ * Python call site it replaces (paths relative to the reference root).
+ *
+ * Layout conventions
+ *   - embedding tables: fp32, row-major [rows, d], rows 0..U-1 users, U..U+I-1 items
+ *     (the reference's torch.cat([user_emb, item_emb]), LightGCN.py:69).
+ *   - adjacency: CSR, int32 rowptr[n+1], int32 colidx[nnz], fp32 vals[nnz]
+ *     (scipy CSR of data/graph.py:10-24, indices sorted within a row).
+ *   - d (embedding.size) must be one of 32, 64, 128.
+ */
+#ifndef SELFREC_B200_H
+#define SELFREC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRB_OK 0
+#define SRB_ERR_ARG (-1)   /* bad argument (shape, null pointer, unsupported d/k) */
+#define SRB_ERR_CUDA (-2)  /* CUDA runtime error or no device */
+#define SRB_ERR_STATE (-3) /* handle misuse */
+
+const char* srb_last_error(void);
+int srb_version(void);
+/* Number of kernel launches issued through this library since load (bench `gpu_launches`). */
+int64_t srb_launch_count(void);
+/* 0 when a CUDA device is usable, SRB_ERR_CUDA otherwise. */
+int srb_device_ok(void);
+
+/* ---------------------------------------------------------------------------------------
+ * (i) Propagation: Y = A * X with a fused epilogue.
+ * Replaces torch.sparse.mm(self.sparse_norm_adj, ego_embeddings)
+ *   LightGCN.py:72, SimGCL.py:85, XSimGCL.py:88, SGL.py:104-108
+ * and the elementwise ops that follow it in the encoders:
+ *   noise      XSimGCL.py:90-91 / SimGCL.py:87-88   y += sign(y) * normalize(noise) * eps
+ *   layer sum  LightGCN.py:74-75 / XSimGCL.py:95-96 (torch.stack + torch.mean)
+ *   Adam       torch.optim.Adam.step (XSimGCL.py:25,37) when the product is the E0 gradient.
+ * ------------------------------------------------------------------------------------- */
+typedef struct srb_spmm_desc {
+  /* A: CSR [n_rows, n_cols] */
+  const int32_t* rowptr;
+  const int32_t* colidx;
+  const float* vals;
+  int32_t n_rows;
+  int32_t n_cols;
+  int32_t d;
+  /* optional processing order of rows (length n_rows), NULL = natural order */
+  const int32_t* row_order;
+  const float* X;     /* [n_cols, d] */
+  float* Y;           /* [n_rows, d] or NULL (result only feeds sum/adam) */
+  const float* extra; /* optional dense addend [n_rows, d]: y += extra_scale * extra[row] */
+  float extra_scale;
+  /* noise epilogue: 0 none, 1 tensor (parity mode), 2 in-kernel Philox (perf mode) */
+  int32_t noise_mode;
+  const float* noise; /* [n_rows, d] uniform [0,1) when noise_mode == 1 */
+  float eps;
+  uint64_t philox_seed;   /* noise_mode == 2 */
+  uint64_t philox_offset; /* distinct per (layer, view) */
+  const int32_t* philox_step_dev; /* optional device step counter mixed into the counter */
+  /* running layer sum: sum_out[row] = sum_scale * ((sum_in ? sum_in[row] : 0) + y) */
+  const float* sum_in;
+  float* sum_out;
+  float sum_scale;
+  /* fused Adam on (p, m, v) with gradient y (after extra); scalars from srb_adam_prepare */
+  float* adam_p;
+  float* adam_m;
+  float* adam_v;
+  const float* adam_scalars; /* device: {step_size, bias_correction2_sqrt} */
+  float beta1, beta2, adam_eps;
+} srb_spmm_desc;
+
+int srb_spmm_csr(const srb_spmm_desc* desc, void* stream);
+
+/* Encoder forward (R4).  Composes srb_spmm_csr launches:
+ *   LGCN_Encoder.forward LightGCN.py:68-78, SGL_Encoder.forward SGL.py:98-113  (include_ego=1)
+ *   SimGCL_Encoder.forward SimGCL.py:81-93, XSimGCL_Encoder.forward XSimGCL.py:83-101 (include_ego=0)
+ * final = mean over layers; cl_view = (perturbed) output of layer layer_cl (1-based), or E0
+ * if layer_cl is never reached (XSimGCL.py:86).  work0/work1: [n, d] ping-pong buffers.
+ * noise (noise_mode==1): [n_layers, n, d]. */
+typedef struct srb_encoder_desc {
+  const int32_t* rowptr;
+  const int32_t* colidx;
+  const float* vals;
+  const int32_t* row_order;
+  int32_t n;
+  int32_t d;
+  int32_t n_layers;
+  int32_t include_ego;
+  int32_t layer_cl; /* 0 = no CL view requested */
+  int32_t noise_mode;
+  const float* noise;
+  float eps;
+  uint64_t philox_seed;
+  uint64_t philox_offset;
+  const int32_t* philox_step_dev;
+  const float* E0; /* [n, d] parameters */
+  float* final_out; /* [n, d] */
+  float* cl_out;    /* [n, d] or NULL */
+  float* work0;
+  float* work1;
+} srb_encoder_desc;
+
+int srb_encoder_forward(const srb_encoder_desc* desc, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * (ii) Fused (u,i,j) gather + BPR + L2 forward/backward.
+ * Replaces   rec_user_emb[user_idx] ...          XSimGCL.py:30 (and peers)
+ *            bpr_loss                            util/loss_torch.py:6-10
+ *            l2_reg_loss                         util/loss_torch.py:18-22
+ * and their autograd backward.  Two launches (the un-squared Frobenius norm needs a
+ * grid-wide reduction before its gradient).
+ *   emb      [n, d] table the (u,i,j) rows are gathered from (item rows offset by n_users)
+ *   l2_emb   table the L2 term gathers from (== emb except LightGCN.py:25 -> raw params)
+ *   l2_terms 2: (u,i)   3: (u,i,j);   l2_div: extra divisor (batch_size or 1)
+ * Outputs: losses[0]=bpr mean, losses[1]=l2 term (reg * sum ||.||_F / rows / l2_div)
+ *   g_emb   [3, b, d] gradient w.r.t. gathered emb rows (u, i, j)
+ *   g_l2    [3, b, d] gradient w.r.t. gathered l2_emb rows (NULL => added into g_emb;
+ *           only valid when l2_emb == emb)
+ *   scratch [8] floats device workspace (zeroed by the call)
+ * ------------------------------------------------------------------------------------- */
+typedef struct srb_bpr_desc {
+  const float* emb;
+  const float* l2_emb;
+  int32_t n_users;
+  int32_t d;
+  const int32_t* u_idx;
+  const int32_t* i_idx;
+  const int32_t* j_idx;
+  const int32_t* b_dev; /* optional device batch size (<= b); NULL => b */
+  int32_t b;
+  float emb_scale; /* gathered rows are emb_scale * emb[row] (lazy layer mean) */
+  float reg;
+  int32_t l2_terms;
+  float l2_div;
+  float grad_scale; /* upstream dLoss (1.0) */
+  float* losses;    /* [2] device */
+  float* g_emb;
+  float* g_l2;
+  float* scratch;
+} srb_bpr_desc;
+
+int srb_bpr_l2_fwd_bwd(const srb_bpr_desc* desc, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * (iii) Fused InfoNCE forward/backward over in-batch negatives.
+ * Replaces InfoNCE(view1[idx], view2[idx], temperature) util/loss_torch.py:35-50 as used by
+ *   XSimGCL.py:45-50, SimGCL.py:43-50, SGL.py:115-125 (and its autograd backward).
+ * The n x n logit matrix never reaches HBM.  A "problem" is one InfoNCE call; several
+ * problems run in one launch sequence (user + item terms).
+ *   view rows are gathered: v1 = scale1 * table1[idx[i] + row_off1], v2 likewise.
+ *   loss_p = mean_i(logsumexp_j S_ij - S_ii),  S = normalize(v1) normalize(v2)^T / tau
+ *   losses[p] device output; g1/g2 [n, d] gradients w.r.t. the gathered rows times weight.
+ * workspace: srb_infonce_workspace_bytes(max_n, d, n_problems) bytes, device.
+ * ------------------------------------------------------------------------------------- */
+typedef struct srb_infonce_problem {
+  const float* table1;
+  const float* table2;
+  int32_t row_off1;
+  int32_t row_off2;
+  float scale1;
+  float scale2;
+  const int32_t* idx;   /* [n] device row ids */
+  const int32_t* n_dev; /* optional device count (<= n) */
+  int32_t n;
+  float weight; /* gradient/loss weight (lambda); loss output is unweighted */
+  float* g1;    /* [n, d] */
+  float* g2;    /* [n, d] */
+  float* loss;  /* [1] */
+} srb_infonce_problem;
+
+typedef struct srb_infonce_desc {
+  int32_t n_problems; /* <= 4 */
+  int32_t d;
+  int32_t b_cos;
+  float temperature;
+  srb_infonce_problem prob[4];
+  void* workspace;
+  int64_t workspace_bytes;
+} srb_infonce_desc;
+
+int64_t srb_infonce_workspace_bytes(int32_t max_n, int32_t d, int32_t n_problems);
+int srb_infonce_fwd_bwd(const srb_infonce_desc* desc, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Sparse-row scatter: dst[rows[r] + row_off] += scale * src[r]  (atomic; duplicates sum).
+ * Replaces the index_put_(accumulate=True) autograd backward of tensor[list] gathers
+ *   (MF.py:20, LightGCN.py:24, XSimGCL.py:30).
+ * ------------------------------------------------------------------------------------- */
+int srb_scatter_add_rows(float* dst, int32_t d, const float* src, const int32_t* rows,
+                         int32_t n, const int32_t* n_dev, int32_t row_off, float scale,
+                         void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Adam (R10): torch.optim.Adam defaults, dense (MF.py:15 ... XSimGCL.py:25).
+ * srb_adam_prepare: one tiny launch; increments the device step counter and writes
+ *   scalars = {lr / (1 - beta1^t), sqrt(1 - beta2^t)} (double arithmetic, like torch's
+ *   Python-float bias corrections).
+ * srb_adam_step: p,m,v update from dense gradient g over n elements.
+ * ------------------------------------------------------------------------------------- */
+int srb_adam_prepare(int32_t* step_dev, float* scalars_dev, double lr, double beta1,
+                     double beta2, void* stream);
+int srb_adam_step(float* p, float* m, float* v, const float* g, int64_t n,
+                  const float* scalars_dev, float beta1, float beta2, float eps,
+                  void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * (iv) Full-catalog scoring + rated-item mask + top-k.
+ * Replaces the per-user loop of GraphRecommender.test() base/graph_recommender.py:38-58:
+ *   predict (XSimGCL.py:57-60), mask -10e8 (graph_recommender.py:48-50),
+ *   find_k_largest util/algorithm.py:144-156.
+ *   user_emb [n_users_total, d], item_emb [n_items, d]
+ *   users    [n_q] user ids to score (test_set order)
+ *   rated_ptr/rated_idx: CSR over ALL users of sorted rated item ids (interaction_mat)
+ *   out_ids  [n_q, k] int32, out_scores [n_q, k] fp32, score-descending
+ * Selection follows find_k_largest's sequential semantics (strict > threshold, evict the
+ * lexicographically smallest (score, id)); scores are exact fp32 fma chains over d.
+ * k <= 32 in this version.
+ * ------------------------------------------------------------------------------------- */
+typedef struct srb_topk_desc {
+  const float* user_emb;
+  const float* item_emb;
+  int32_t n_items;
+  int32_t d;
+  const int32_t* users;
+  int32_t n_q;
+  const int32_t* rated_ptr;
+  const int32_t* rated_idx;
+  int32_t k;
+  int32_t* out_ids;
+  float* out_scores;
+  int32_t impl; /* 0 auto, 1 cuda-core fp32, 2 tcgen05 3xTF32 + exact rescoring */
+  void* workspace; /* impl 2: srb_topk_workspace_bytes */
+  int64_t workspace_bytes;
+} srb_topk_desc;
+
+int64_t srb_topk_workspace_bytes(int32_t n_q, int32_t n_items, int32_t d, int32_t k);
+int srb_score_topk(const srb_topk_desc* desc, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * One whole training step (R3-R8, R10) as a single call: forward propagation, gather +
+ * BPR + L2, InfoNCE, Horner backward through the propagation, Adam in the epilogue of the
+ * last backward SpMM.  Replaces the body of <Model>.train()'s batch loop:
+ *   MF.py:17-25  LightGCN.py:21-29  SimGCL.py:25-36  XSimGCL.py:27-37  SGL.py:30-41
+ * The call only enqueues work (graph-capturable); batch indices live in one device
+ * buffer laid out by srb_sampler_next_batch (header + u,i,j + unique lists).
+ * ------------------------------------------------------------------------------------- */
+enum { SRB_MODEL_MF = 0, SRB_MODEL_LIGHTGCN = 1, SRB_MODEL_SIMGCL = 2, SRB_MODEL_XSIMGCL = 3, SRB_MODEL_SGL = 4 };
+
+typedef struct srb_graph_csr {
+  const int32_t* rowptr;
+  const int32_t* colidx;
+  const float* vals;
+  const int32_t* row_order;
+} srb_graph_csr;
+
+typedef struct srb_step_desc {
+  int32_t model;
+  int32_t n_users, n_items, d, n_layers;
+  int32_t batch_cap;       /* B: capacity of the batch buffer sections */
+  int32_t layer_cl;        /* XSimGCL l_star */
+  float eps, tau, cl_rate; /* noise magnitude, temperature, lambda */
+  float reg;
+  double lr, beta1, beta2;
+  float adam_eps;
+  float l2_div;            /* configured batch.size where the model divides by it, else 1 */
+  int32_t noise_mode;      /* 1 tensor, 2 philox */
+  const float* noise;      /* mode 1: [views, n_layers, n, d] */
+  uint64_t philox_seed;
+  srb_graph_csr adj;       /* clean normalised adjacency */
+  srb_graph_csr adj_view[2]; /* SGL: the two dropped graphs */
+  const int32_t* batch;    /* device batch buffer (see srb_batch_layout) */
+  float* params;           /* [n, d] E0 (updated in place) */
+  float* adam_m;
+  float* adam_v;
+  int32_t* step_dev;       /* device step counter */
+  float* scalars;          /* [16] device scratch for adam scalars + loss accumulators */
+  float* losses;           /* [4] device: rec (bpr), l2, cl (weighted), total */
+  void* workspace;
+  int64_t workspace_bytes; /* >= srb_step_workspace_bytes */
+} srb_step_desc;
+
+int64_t srb_step_workspace_bytes(int32_t model, int32_t n, int32_t d, int32_t batch_cap);
+int srb_train_step(const srb_step_desc* desc, void* stream);
+
+/* batch buffer layout (int32 words): [0]=b [1]=n_uniq_u [2]=n_uniq_i [3]=reserved
+ * then 5 sections of batch_cap words: u_idx, i_idx, j_idx, uniq_u, uniq_i. */
+#define SRB_BATCH_HEADER 4
+static inline int64_t srb_batch_words(int32_t batch_cap) { return SRB_BATCH_HEADER + 5ll * batch_cap; }
+
+/* ---------------------------------------------------------------------------------------
+ * (R1) Pairwise sampler, host side, bit-exact with CPython's `random` stream.
+ * Replaces next_batch_pairwise util/sampler.py:5-28 : random.shuffle (in place, persists
+ * across epochs) + per positive `choice(item_list)` re-drawn while (u, j) in train.
+ * The MT19937 state is imported from / exported to random.getstate() (625 words:
+ * 624 state + index) so the Python-visible stream stays identical to the reference's.
+ * ------------------------------------------------------------------------------------- */
+typedef struct srb_sampler srb_sampler;
+
+/* users/items: the training pairs (internal ids) in training_data order; copied. */
+srb_sampler* srb_sampler_create(const int32_t* users, const int32_t* items, int64_t n_pairs,
+                                int32_t n_users, int32_t n_items);
+void srb_sampler_destroy(srb_sampler* s);
+int srb_sampler_set_state(srb_sampler* s, const uint32_t* mt625);
+int srb_sampler_get_state(const srb_sampler* s, uint32_t* mt625);
+/* Start an epoch: shuffles the pair order exactly like random.shuffle(training_data).
+ * perm_out (optional, n_pairs int64): new_order[k] = index into the PREVIOUS order. */
+int srb_sampler_begin_epoch(srb_sampler* s, int64_t* perm_out);
+/* Next batch into `out` (srb_batch_words(batch_cap) int32 words, host).  Returns the
+ * batch size b (0 when the epoch is exhausted), negative on error.  n_negs == 1. */
+int srb_sampler_next_batch(srb_sampler* s, int32_t batch_size, int32_t batch_cap, int32_t* out);
+/* Whole-epoch variant: fills out[n_batches * srb_batch_words(batch_cap)]; returns n_batches. */
+int64_t srb_sampler_epoch(srb_sampler* s, int32_t batch_size, int32_t batch_cap, int32_t* out,
+                          int64_t out_words);
+int64_t srb_sampler_pairs(const srb_sampler* s);
+
+/* ---------------------------------------------------------------------------------------
+ * Row-sharded multi-GPU propagation.  rank r owns rows [row_begin, row_end);
+ * the epilogue stores every finished row into each peer's copy of the layer output
+ * (peer_Y[g], NVLink P2P stores) so the all-gather is fused into the SpMM.
+ * ------------------------------------------------------------------------------------- */
+typedef struct srb_spmm_sharded_desc {
+  srb_spmm_desc local; /* rowptr sliced for the owned rows; Y ignored */
+  int32_t row_begin;   /* global index of local row 0 */
+  int32_t world;
+  float* peer_Y[8];    /* full [n_cols, d] buffers on every rank (own rank included) */
+} srb_spmm_sharded_desc;
+
+int srb_spmm_csr_allgather(const srb_spmm_sharded_desc* desc, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SELFREC_B200_H */

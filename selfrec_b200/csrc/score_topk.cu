@@ -1,0 +1,205 @@
+// (iv) Full-catalog scoring + rated-item mask + top-k   (impl 1: CUDA-core fp32).
+//
+// Replaces the per-user loop of GraphRecommender.test() base/graph_recommender.py:38-58:
+//   candidates = predict(user)            XSimGCL.py:57-60  (user_emb[u] @ item_emb.T)
+//   candidates[rated] = -10e8             graph_recommender.py:48-50
+//   find_k_largest(max_N, candidates)     util/algorithm.py:144-156
+//
+// One CTA scores 32 users against the whole catalogue in tiles of 128 items.  Each score is
+// an fp32 fma chain over k = 0..d-1 (exactly the oracle's loop, so scores are bit-identical).
+// The warp that computed a user's scores also owns that user's top-k list: one list entry
+// per lane, kept sorted by (score desc, id desc); a candidate enters iff score > current
+// k-th score (strict, like the reference's heapreplace test) and the last entry -- the
+// lexicographically smallest (score, id), i.e. what heapq would pop -- is evicted.  Items
+// are visited in id order, so the final SET equals find_k_largest's, ties included.
+#include "common.cuh"
+
+namespace srb {
+
+constexpr int TK_TM = 32;   // users per CTA
+constexpr int TK_TN = 128;  // items per tile
+constexpr float TK_MASKED = -1e9f;  // -10e8
+
+struct TopkArgs {
+  const float* user_emb;
+  const float* item_emb;
+  int32_t n_items;
+  const int32_t* users;
+  int32_t n_q;
+  const int32_t* rated_ptr;
+  const int32_t* rated_idx;
+  int32_t k;
+  int32_t* out_ids;
+  float* out_scores;
+};
+
+template <int D>
+__global__ void __launch_bounds__(256) score_topk_kernel(const TopkArgs a) {
+  extern __shared__ __align__(16) float tk_smem[];
+  float (*Us)[TK_TM] = reinterpret_cast<float (*)[TK_TM]>(tk_smem);                   // [D][32] k-major
+  float (*Is)[D + 1] = reinterpret_cast<float (*)[D + 1]>(tk_smem + D * TK_TM);       // [128][D+1]
+  const int lane = threadIdx.x & 31;
+  const int ty = threadIdx.x >> 5;  // warp id: users ty*4 .. ty*4+3 of the CTA tile
+  const int q0 = blockIdx.x * TK_TM;
+
+  // user tile (gathered by id), transposed to k-major
+  for (int e = threadIdx.x; e < TK_TM * (D / 4); e += blockDim.x) {
+    const int u = e % TK_TM, k4 = e / TK_TM;
+    float4 v = f4_zero();
+    if (q0 + u < a.n_q) v = ldg4(a.user_emb + (size_t)a.users[q0 + u] * D + k4 * 4);
+    Us[k4 * 4 + 0][u] = v.x;
+    Us[k4 * 4 + 1][u] = v.y;
+    Us[k4 * 4 + 2][u] = v.z;
+    Us[k4 * 4 + 3][u] = v.w;
+  }
+
+  // per-user state of this warp: sorted list entry per lane, mask cursor
+  float ls[4];
+  int li[4];
+  int cur[4], cend[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    ls[r] = -INFINITY;
+    li[r] = -1;
+    const int q = q0 + ty * 4 + r;
+    if (q < a.n_q && a.rated_ptr) {
+      const int u = a.users[q];
+      cur[r] = a.rated_ptr[u];
+      cend[r] = a.rated_ptr[u + 1];
+    } else {
+      cur[r] = cend[r] = 0;
+    }
+  }
+  const int K = a.k;
+
+  for (int n0 = 0; n0 < a.n_items; n0 += TK_TN) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < TK_TN * (D / 4); e += blockDim.x) {
+      const int row = e / (D / 4), c4 = e % (D / 4);
+      float4 v = f4_zero();
+      if (n0 + row < a.n_items) v = ldg4(a.item_emb + (size_t)(n0 + row) * D + c4 * 4);
+      Is[row][c4 * 4 + 0] = v.x;
+      Is[row][c4 * 4 + 1] = v.y;
+      Is[row][c4 * 4 + 2] = v.z;
+      Is[row][c4 * 4 + 3] = v.w;
+    }
+    __syncthreads();
+    float s[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) s[r][c] = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < D; ++k) {
+      const float4 uv = *reinterpret_cast<const float4*>(&Us[k][ty * 4]);
+      const float ur[4] = {uv.x, uv.y, uv.z, uv.w};
+      float iv[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) iv[c] = Is[lane + 32 * c][k];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) s[r][c] = fmaf(ur[r], iv[c], s[r][c]);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      // items past the end of the catalogue can never enter
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (n0 + lane + 32 * c >= a.n_items) s[r][c] = -INFINITY;
+      // rated-item mask: walk this user's sorted rated list through the tile
+      while (true) {
+        const int pos = cur[r] + lane;
+        int e = (pos < cend[r]) ? a.rated_idx[pos] : 0x7fffffff;
+        const unsigned in = __ballot_sync(SRB_FULL_MASK, e < n0 + TK_TN);
+        const int cnt = __popc(in);
+        for (int t = 0; t < cnt; ++t) {
+          const int et = __shfl_sync(SRB_FULL_MASK, e, t) - n0;
+          if (et >= 0 && (et & 31) == lane) {
+            const int c = et >> 5;
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc)
+              if (cc == c) s[r][cc] = TK_MASKED;
+          }
+        }
+        cur[r] += cnt;
+        if (cnt < 32) break;
+      }
+      // sequential (id-ordered) insertion, 32 candidates per round
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float sc = s[r][c];
+        const int id = n0 + lane + 32 * c;
+        float thr = __shfl_sync(SRB_FULL_MASK, ls[r], K - 1);
+        unsigned m = __ballot_sync(SRB_FULL_MASK, sc > thr);
+        while (m) {
+          const int src = __ffs(m) - 1;
+          m &= m - 1;
+          const float cs = __shfl_sync(SRB_FULL_MASK, sc, src);
+          const int cid = __shfl_sync(SRB_FULL_MASK, id, src);
+          thr = __shfl_sync(SRB_FULL_MASK, ls[r], K - 1);
+          if (cs > thr) {
+            const int pos = __popc(__ballot_sync(SRB_FULL_MASK, lane < K && ls[r] > cs));
+            const float ps = __shfl_up_sync(SRB_FULL_MASK, ls[r], 1);
+            const int pi = __shfl_up_sync(SRB_FULL_MASK, li[r], 1);
+            if (lane > pos && lane < K) ls[r] = ps, li[r] = pi;
+            if (lane == pos) ls[r] = cs, li[r] = cid;
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int q = q0 + ty * 4 + r;
+    if (q < a.n_q && lane < K) {
+      a.out_ids[(size_t)q * K + lane] = li[r];
+      a.out_scores[(size_t)q * K + lane] = ls[r];
+    }
+  }
+}
+
+int score_topk_tc(const srb_topk_desc* d, cudaStream_t st);  // score_topk_tc.cu
+
+template <int D>
+static int launch_topk(const TopkArgs& a, cudaStream_t st) {
+  const size_t smem = sizeof(float) * (D * TK_TM + TK_TN * (D + 1));
+  static bool attr_done = false;
+  if (!attr_done) {
+    SRB_TRY(check_cuda(cudaFuncSetAttribute(score_topk_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "topk smem attr"));
+    attr_done = true;
+  }
+  const int blocks = (a.n_q + TK_TM - 1) / TK_TM;
+  score_topk_kernel<D><<<blocks, 256, smem, st>>>(a);
+  return post_launch("score_topk_kernel");
+}
+
+}  // namespace srb
+
+extern "C" int srb_score_topk(const srb_topk_desc* d, void* stream) {
+  SRB_REQUIRE(d != nullptr, "topk: null desc");
+  SRB_REQUIRE(d->user_emb && d->item_emb && d->users && d->out_ids && d->out_scores, "topk: null pointer");
+  SRB_REQUIRE((d->rated_ptr == nullptr) == (d->rated_idx == nullptr), "topk: rated_ptr/rated_idx must both be set or both null");
+  SRB_REQUIRE(d->k >= 1 && d->k <= 32, "topk: k=%d unsupported (1..32)", d->k);
+  SRB_REQUIRE(d->n_items >= 1 && d->n_q >= 0, "topk: bad shape");
+  SRB_REQUIRE(d->impl >= 0 && d->impl <= 2, "topk: bad impl");
+  if (d->n_q == 0) return SRB_OK;
+  if (d->impl == 2) return srb::score_topk_tc(d, (cudaStream_t)stream);
+  srb::TopkArgs a;
+  a.user_emb = d->user_emb;
+  a.item_emb = d->item_emb;
+  a.n_items = d->n_items;
+  a.users = d->users;
+  a.n_q = d->n_q;
+  a.rated_ptr = d->rated_ptr;
+  a.rated_idx = d->rated_idx;
+  a.k = d->k;
+  a.out_ids = d->out_ids;
+  a.out_scores = d->out_scores;
+  switch (d->d) {
+    case 32: return srb::launch_topk<32>(a, (cudaStream_t)stream);
+    case 64: return srb::launch_topk<64>(a, (cudaStream_t)stream);
+    case 128: return srb::launch_topk<128>(a, (cudaStream_t)stream);
+    default: srb::set_error("topk: unsupported d=%d (32, 64, 128)", d->d); return SRB_ERR_ARG;
+  }
+}
