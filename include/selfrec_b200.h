@@ -193,6 +193,15 @@ typedef struct srb_infonce_desc {
 int64_t srb_infonce_workspace_bytes(int32_t max_n, int32_t d, int32_t n_problems);
 int srb_infonce_fwd_bwd(const srb_infonce_desc* desc, void* stream);
 
+/* Standalone l2_reg_loss (util/loss_torch.py:18-22) on already-gathered embeddings, for the
+ * op-level drop-in: loss = reg * sum_t ||x_t||_F / rows_t.  sumsq_dev: [4] device scratch kept
+ * for the backward; gout_dev: device scalar upstream gradient. */
+int srb_l2_reg_fwd(int32_t n_terms, const float* const* x, const int64_t* n_elems, const int32_t* rows,
+                   float reg, float* sumsq_dev, float* loss_dev, void* stream);
+int srb_l2_reg_bwd(int32_t n_terms, const float* const* x, float* const* g, const int64_t* n_elems,
+                   const int32_t* rows, float reg, const float* sumsq_dev, const float* gout_dev,
+                   void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Sparse-row scatter: dst[rows[r] + row_off] += scale * src[r]  (atomic; duplicates sum).
  * Replaces the index_put_(accumulate=True) autograd backward of tensor[list] gathers
@@ -247,6 +256,14 @@ typedef struct srb_topk_desc {
 
 int64_t srb_topk_workspace_bytes(int32_t n_q, int32_t n_items, int32_t d, int32_t k);
 int srb_score_topk(const srb_topk_desc* desc, void* stream);
+/* Mask-free top-k of precomputed score rows [n_q, n_items] (models whose predict() is not one
+ * dot product, e.g. BUIR.py); same selection rule.  The caller applies the -10e8 mask. */
+/* Dense score rows out[q, i] = <user_emb[users[q]], item_emb[i]>, the reference's predict()
+ * (XSimGCL.py:57-60); same fp32 fma chain as srb_score_topk. */
+int srb_score_rows(const float* user_emb, const float* item_emb, int32_t d, const int32_t* users,
+                   int32_t n_q, int32_t n_items, float* out, void* stream);
+int srb_topk_rows(const float* scores, int32_t n_q, int32_t n_items, int32_t k, int32_t* out_ids,
+                  float* out_scores, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * One whole training step (R3-R8, R10) as a single call: forward propagation, gather +
@@ -320,6 +337,9 @@ int srb_sampler_begin_epoch(srb_sampler* s, int64_t* perm_out);
 /* Next batch into `out` (srb_batch_words(batch_cap) int32 words, host).  Returns the
  * batch size b (0 when the epoch is exhausted), negative on error.  n_negs == 1. */
 int srb_sampler_next_batch(srb_sampler* s, int32_t batch_size, int32_t batch_cap, int32_t* out);
+/* General form: n_negs >= 1, separate arrays u[b], i[b], j[b * n_negs] (sampler.py:23-27). */
+int srb_sampler_next_batch_negs(srb_sampler* s, int32_t batch_size, int32_t n_negs, int32_t* u,
+                                int32_t* i, int32_t* j);
 /* Whole-epoch variant: fills out[n_batches * srb_batch_words(batch_cap)]; returns n_batches. */
 int64_t srb_sampler_epoch(srb_sampler* s, int32_t batch_size, int32_t batch_cap, int32_t* out,
                           int64_t out_words);

@@ -195,6 +195,51 @@ int scatter_segments(float* dst, int d, const ScatterSegs& segs, cudaStream_t st
   return post_launch("scatter_add_rows_kernel");
 }
 
+// Standalone l2_reg_loss (util/loss_torch.py:18-22) for the op-level drop-in, where the
+// embeddings arrive already gathered: sumsq[t] = ||e_t||_F^2 (atomic), then
+// loss = reg * sum_t sqrt(sumsq[t]) / rows_t and grad_t = g * reg / rows_t * e_t / ||e_t||_F.
+struct L2Args {
+  int n_terms;
+  const float* x[4];
+  float* g[4];
+  long long n[4];   // elements
+  int rows[4];
+};
+
+__global__ void __launch_bounds__(256) l2_sumsq_kernel(const L2Args a, float* sumsq) {
+  const int t = blockIdx.y;
+  const long long n = a.n[t];
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = a.x[t][i];
+    acc = fmaf(v, v, acc);
+  }
+  acc = warp_sum(acc);
+  __shared__ float red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+    atomicAdd(sumsq + t, s);
+  }
+}
+
+__global__ void l2_loss_kernel(const L2Args a, const float* sumsq, float reg, float* loss) {
+  float l = 0.f;
+  for (int t = 0; t < a.n_terms; ++t) l += sqrtf(sumsq[t]) / (float)a.rows[t];
+  *loss = l * reg;
+}
+
+__global__ void __launch_bounds__(256) l2_grad_kernel(const L2Args a, const float* sumsq, float reg, const float* gout) {
+  const int t = blockIdx.y;
+  const long long n = a.n[t];
+  const float nrm = sqrtf(sumsq[t]);
+  const float k = (nrm > 0.f) ? (*gout) * reg / ((float)a.rows[t] * nrm) : 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    a.g[t][i] = k * a.x[t][i];
+}
+
 __global__ void adam_prepare_kernel(int32_t* step, float* scalars, double lr, double b1, double b2) {
   const int t = *step + 1;
   *step = t;
@@ -310,4 +355,49 @@ extern "C" int srb_adam_step(float* p, float* m, float* v, const float* g, int64
   if (blocks < 1) blocks = 1;
   srb::adam_step_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p, m, v, g, n4, n, scalars_dev, beta1, beta2, eps);
   return srb::post_launch("adam_step_kernel");
+}
+
+extern "C" int srb_l2_reg_fwd(int32_t n_terms, const float* const* x, const int64_t* n_elems, const int32_t* rows, float reg,
+                              float* sumsq_dev, float* loss_dev, void* stream) {
+  SRB_REQUIRE(n_terms >= 1 && n_terms <= 4, "l2_reg: 1..4 terms");
+  SRB_REQUIRE(x && n_elems && rows && sumsq_dev && loss_dev, "l2_reg: null pointer");
+  srb::L2Args a = {};
+  a.n_terms = n_terms;
+  long long mx = 1;
+  for (int t = 0; t < n_terms; ++t) {
+    SRB_REQUIRE(x[t] && rows[t] > 0 && n_elems[t] >= 0, "l2_reg: bad term %d", t);
+    a.x[t] = x[t];
+    a.n[t] = n_elems[t];
+    a.rows[t] = rows[t];
+    if (n_elems[t] > mx) mx = n_elems[t];
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  SRB_TRY(srb::check_cuda(cudaMemsetAsync(sumsq_dev, 0, 4 * sizeof(float), st), "l2 memset"));
+  long long bx = (mx + 255) / 256;
+  if (bx > 1024) bx = 1024;
+  srb::l2_sumsq_kernel<<<dim3((unsigned)bx, n_terms), 256, 0, st>>>(a, sumsq_dev);
+  SRB_TRY(srb::post_launch("l2_sumsq_kernel"));
+  srb::l2_loss_kernel<<<1, 1, 0, st>>>(a, sumsq_dev, reg, loss_dev);
+  return srb::post_launch("l2_loss_kernel");
+}
+
+extern "C" int srb_l2_reg_bwd(int32_t n_terms, const float* const* x, float* const* g, const int64_t* n_elems,
+                              const int32_t* rows, float reg, const float* sumsq_dev, const float* gout_dev, void* stream) {
+  SRB_REQUIRE(n_terms >= 1 && n_terms <= 4, "l2_reg: 1..4 terms");
+  SRB_REQUIRE(x && g && n_elems && rows && sumsq_dev && gout_dev, "l2_reg: null pointer");
+  srb::L2Args a = {};
+  a.n_terms = n_terms;
+  long long mx = 1;
+  for (int t = 0; t < n_terms; ++t) {
+    SRB_REQUIRE(x[t] && g[t] && rows[t] > 0, "l2_reg: bad term %d", t);
+    a.x[t] = x[t];
+    a.g[t] = g[t];
+    a.n[t] = n_elems[t];
+    a.rows[t] = rows[t];
+    if (n_elems[t] > mx) mx = n_elems[t];
+  }
+  long long bx = (mx + 255) / 256;
+  if (bx > 1024) bx = 1024;
+  srb::l2_grad_kernel<<<dim3((unsigned)bx, n_terms), 256, 0, (cudaStream_t)stream>>>(a, sumsq_dev, reg, gout_dev);
+  return srb::post_launch("l2_grad_kernel");
 }

@@ -226,6 +226,43 @@ extern "C" int srb_sampler_next_batch(srb_sampler* s, int32_t batch_size, int32_
   return b;
 }
 
+// General form (n_negs >= 1, separate output arrays): j has b * n_negs entries, the n_negs
+// negatives of positive t at j[t * n_negs ...] exactly like sampler.py:23-27.
+extern "C" int srb_sampler_next_batch_negs(srb_sampler* s, int32_t batch_size, int32_t n_negs, int32_t* u, int32_t* i,
+                                           int32_t* j) {
+  if (!s || !u || !i || !j || batch_size <= 0 || n_negs < 1) {
+    srb::set_error("sampler_next_batch_negs: bad arguments");
+    return SRB_ERR_ARG;
+  }
+  if (!s->epoch_open) {
+    srb::set_error("sampler_next_batch_negs: begin_epoch was not called");
+    return SRB_ERR_STATE;
+  }
+  const int64_t n = (int64_t)s->pu.size();
+  if (s->ptr >= n) {
+    s->epoch_open = false;
+    return 0;
+  }
+  const int64_t end = (s->ptr + batch_size < n) ? s->ptr + batch_size : n;
+  const int b = (int)(end - s->ptr);
+  for (int t = 0; t < b; ++t) {
+    const int32_t user = s->pu[s->ptr + t];
+    u[t] = user;
+    i[t] = s->pi[s->ptr + t];
+    if (s->rated_ptr[user + 1] - s->rated_ptr[user] >= s->n_items) {
+      srb::set_error("sampler_next_batch_negs: user %d has rated every item; no negative exists", user);
+      return SRB_ERR_STATE;
+    }
+    for (int m = 0; m < n_negs; ++m) {
+      int32_t neg = (int32_t)s->randbelow((uint32_t)s->n_items);
+      while (s->rated(user, neg)) neg = (int32_t)s->randbelow((uint32_t)s->n_items);
+      j[(int64_t)t * n_negs + m] = neg;
+    }
+  }
+  s->ptr = end;
+  return b;
+}
+
 extern "C" int64_t srb_sampler_epoch(srb_sampler* s, int32_t batch_size, int32_t batch_cap, int32_t* out, int64_t out_words) {
   if (!s || !out) {
     srb::set_error("sampler_epoch: null");

@@ -159,6 +159,66 @@ __global__ void __launch_bounds__(256) score_topk_kernel(const TopkArgs a) {
   }
 }
 
+// top-k of precomputed score rows (models whose predict() is not a single dot product,
+// SURVEY 8b): one warp per row, same sequential insertion rule as above.
+__global__ void __launch_bounds__(256) topk_rows_kernel(const float* scores, int n_q, int n_items, int k, int32_t* out_ids,
+                                                        float* out_scores) {
+  const int lane = threadIdx.x & 31;
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= n_q) return;
+  float ls = -INFINITY;
+  int li = -1;
+  const float* row = scores + (size_t)q * n_items;
+  for (int n0 = 0; n0 < n_items; n0 += 32) {
+    const int id = n0 + lane;
+    const float sc = (id < n_items) ? row[id] : -INFINITY;
+    float thr = __shfl_sync(SRB_FULL_MASK, ls, k - 1);
+    unsigned m = __ballot_sync(SRB_FULL_MASK, sc > thr);
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      const float cs = __shfl_sync(SRB_FULL_MASK, sc, src);
+      const int cid = __shfl_sync(SRB_FULL_MASK, id, src);
+      thr = __shfl_sync(SRB_FULL_MASK, ls, k - 1);
+      if (cs > thr) {
+        const int pos = __popc(__ballot_sync(SRB_FULL_MASK, lane < k && ls > cs));
+        const float ps = __shfl_up_sync(SRB_FULL_MASK, ls, 1);
+        const int pi = __shfl_up_sync(SRB_FULL_MASK, li, 1);
+        if (lane > pos && lane < k) ls = ps, li = pi;
+        if (lane == pos) ls = cs, li = cid;
+      }
+    }
+  }
+  if (lane < k) {
+    out_ids[(size_t)q * k + lane] = li;
+    out_scores[(size_t)q * k + lane] = ls;
+  }
+}
+
+// dense score rows out[q][i] = <user_emb[users[q]], item_emb[i]> (same fma chain as above):
+// the reference's predict() (XSimGCL.py:57-60) for callers that want the raw vector.
+template <int D>
+__global__ void __launch_bounds__(256) score_rows_kernel(const float* user_emb, const float* item_emb, const int32_t* users,
+                                                         int n_items, float* out) {
+  __shared__ float us[D];
+  const int q = blockIdx.y;
+  for (int k = threadIdx.x; k < D; k += blockDim.x) us[k] = user_emb[(size_t)users[q] * D + k];
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_items) return;
+  const float* it = item_emb + (size_t)i * D;
+  float acc = 0.f;
+#pragma unroll 8
+  for (int k4 = 0; k4 < D / 4; ++k4) {
+    const float4 v = ldg4(it + k4 * 4);
+    acc = fmaf(us[k4 * 4 + 0], v.x, acc);
+    acc = fmaf(us[k4 * 4 + 1], v.y, acc);
+    acc = fmaf(us[k4 * 4 + 2], v.z, acc);
+    acc = fmaf(us[k4 * 4 + 3], v.w, acc);
+  }
+  out[(size_t)q * n_items + i] = acc;
+}
+
 int score_topk_tc(const srb_topk_desc* d, cudaStream_t st);  // score_topk_tc.cu
 
 template <int D>
@@ -202,4 +262,30 @@ extern "C" int srb_score_topk(const srb_topk_desc* d, void* stream) {
     case 128: return srb::launch_topk<128>(a, (cudaStream_t)stream);
     default: srb::set_error("topk: unsupported d=%d (32, 64, 128)", d->d); return SRB_ERR_ARG;
   }
+}
+
+extern "C" int srb_topk_rows(const float* scores, int32_t n_q, int32_t n_items, int32_t k, int32_t* out_ids,
+                             float* out_scores, void* stream) {
+  SRB_REQUIRE(scores && out_ids && out_scores, "topk_rows: null pointer");
+  SRB_REQUIRE(k >= 1 && k <= 32, "topk_rows: k=%d unsupported (1..32)", k);
+  SRB_REQUIRE(n_q >= 0 && n_items >= 1, "topk_rows: bad shape");
+  if (n_q == 0) return SRB_OK;
+  srb::topk_rows_kernel<<<(n_q + 7) / 8, 256, 0, (cudaStream_t)stream>>>(scores, n_q, n_items, k, out_ids, out_scores);
+  return srb::post_launch("topk_rows_kernel");
+}
+
+extern "C" int srb_score_rows(const float* user_emb, const float* item_emb, int32_t d, const int32_t* users, int32_t n_q,
+                              int32_t n_items, float* out, void* stream) {
+  SRB_REQUIRE(user_emb && item_emb && users && out, "score_rows: null pointer");
+  SRB_REQUIRE(n_q >= 0 && n_q <= 65535 && n_items >= 1, "score_rows: bad shape (n_q <= 65535)");
+  if (n_q == 0) return SRB_OK;
+  dim3 grid((n_items + 255) / 256, n_q);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (d) {
+    case 32: srb::score_rows_kernel<32><<<grid, 256, 0, st>>>(user_emb, item_emb, users, n_items, out); break;
+    case 64: srb::score_rows_kernel<64><<<grid, 256, 0, st>>>(user_emb, item_emb, users, n_items, out); break;
+    case 128: srb::score_rows_kernel<128><<<grid, 256, 0, st>>>(user_emb, item_emb, users, n_items, out); break;
+    default: srb::set_error("score_rows: unsupported d=%d (32, 64, 128)", d); return SRB_ERR_ARG;
+  }
+  return srb::post_launch("score_rows_kernel");
 }

@@ -1,0 +1,176 @@
+"""TrainEngine: device state + one fused training step per call (srb_train_step).
+
+Owns (as torch tensors, i.e. PyTorch's allocator) the single contiguous [U+I, d] parameter
+table -- users first, items after, so the reference's torch.cat (LightGCN.py:69) disappears
+-- the Adam moments, the step counter, the workspace and the device batch buffer.  step()
+enqueues one H2D copy of the batch words plus the whole forward/backward/Adam sequence on
+the current stream; nothing synchronises.  capture() wraps the same sequence in a CUDA graph.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from .util.sampler import NativePairSampler
+
+
+class TrainEngine:
+    def __init__(self, model, data, emb_size, n_layers, batch_size, lr, reg, *, eps=0.0, tau=0.2, cl_rate=0.0,
+                 layer_cl=0, l2_div=1.0, device=None, init_user=None, init_item=None, philox_seed=0x5EED):
+        lib = _lib.require_device()
+        self.lib = lib
+        self.model_name = model
+        self.model_id = _lib.MODEL_IDS[model]
+        self.data = data
+        self.U, self.I, self.d = int(data.user_num), int(data.item_num), int(emb_size)
+        self.N = self.U + self.I
+        self.L = int(n_layers) if model != "MF" else 0
+        self.B = int(batch_size)
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        dev = self.dev
+        if init_user is None:  # same initialiser calls, same order as LightGCN.py:60-66
+            init_user = torch.nn.init.xavier_uniform_(torch.empty(self.U, self.d))
+            init_item = torch.nn.init.xavier_uniform_(torch.empty(self.I, self.d))
+        self.params = torch.empty((self.N, self.d), device=dev, dtype=torch.float32)
+        self.params[: self.U].copy_(init_user)
+        self.params[self.U:].copy_(init_item)
+        self.m = torch.zeros_like(self.params)
+        self.v = torch.zeros_like(self.params)
+        self.step_dev = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.scalars = torch.zeros(16, device=dev, dtype=torch.float32)
+        self.losses = torch.zeros(4, device=dev, dtype=torch.float32)
+        self.words = _lib.BATCH_HEADER + 5 * self.B
+        self.batch_dev = torch.zeros(self.words, device=dev, dtype=torch.int32)
+        self.ring = [torch.zeros(self.words, dtype=torch.int32).pin_memory() for _ in range(8)]
+        self.ring_ev = [None] * len(self.ring)
+        self.ring_pos = 0
+        ws_bytes = lib.srb_step_workspace_bytes(self.model_id, self.N, self.d, self.B)
+        self.workspace = torch.empty(ws_bytes + 256, device=dev, dtype=torch.uint8)
+        ws_ptr = (self.workspace.data_ptr() + 255) // 256 * 256
+        self.adj = None
+        if model != "MF":
+            self.adj = ops.SparseAdj(data.norm_adj).cuda(dev)
+        self.view_adj = [None, None]
+        self.noise = None
+        s = _lib.StepDesc()
+        s.model, s.n_users, s.n_items, s.d, s.n_layers = self.model_id, self.U, self.I, self.d, self.L
+        s.batch_cap, s.layer_cl = self.B, int(layer_cl)
+        s.eps, s.tau, s.cl_rate, s.reg = float(eps), float(tau), float(cl_rate), float(reg)
+        s.lr, s.beta1, s.beta2, s.adam_eps = float(lr), 0.9, 0.999, 1e-8
+        s.l2_div = float(l2_div)
+        s.noise_mode = 2 if model in ("SimGCL", "XSimGCL") else 0
+        s.philox_seed = int(philox_seed)
+        if self.adj is not None:
+            s.adj = self.adj.graph_struct()
+        s.batch, s.params, s.adam_m, s.adam_v = ops._p(self.batch_dev), ops._p(self.params), ops._p(self.m), ops._p(self.v)
+        s.step_dev, s.scalars, s.losses = ops._p(self.step_dev), ops._p(self.scalars), ops._p(self.losses)
+        s.workspace, s.workspace_bytes = C.c_void_p(ws_ptr), ws_bytes
+        self.desc = s
+        self.eps, self.layer_cl = float(eps), int(layer_cl)
+        self.sampler = None
+        self.graph = None
+
+    # ---- parameters as the reference exposes them ------------------------------------
+    @property
+    def user_emb(self):
+        return self.params[: self.U]
+
+    @property
+    def item_emb(self):
+        return self.params[self.U:]
+
+    # ---- configuration -----------------------------------------------------------------
+    def set_noise_tensor(self, noise):
+        """Parity mode: noise is an INPUT, uniform[0,1) of shape [views, L, N, d]."""
+        noise = ops._f32c(noise, "noise")
+        views = 2 if self.model_name == "SimGCL" else 1
+        if tuple(noise.shape) != (views, self.L, self.N, self.d):
+            raise ValueError(f"noise must be [{views}, {self.L}, {self.N}, {self.d}]")
+        self.noise = noise
+        self.desc.noise_mode, self.desc.noise = 1, ops._p(noise)
+
+    def set_view_graphs(self, adj1, adj2):
+        """SGL: the two dropped, re-normalised graphs of this epoch (SGL.py:27-29)."""
+        self.view_adj = [a if isinstance(a, ops.SparseAdj) else ops.SparseAdj(a) for a in (adj1, adj2)]
+        for k, a in enumerate(self.view_adj):
+            a.cuda(self.dev)
+            self.desc.adj_view[k] = a.graph_struct()
+        self.graph = None  # pointers changed: a captured graph is stale
+
+    # ---- stepping ------------------------------------------------------------------------
+    def _enqueue(self):
+        _lib.check(self.lib.srb_train_step(C.byref(self.desc), ops._stream()), "srb_train_step")
+
+    def step(self, batch_words):
+        """batch_words: int32 array/tensor of `words` entries laid out by srb_sampler_next_batch."""
+        slot = self.ring_pos
+        self.ring_pos = (slot + 1) % len(self.ring)
+        ev = self.ring_ev[slot]
+        if ev is not None:
+            ev.synchronize()  # the copy that last used this pinned slot has finished
+        pin = self.ring[slot]
+        if isinstance(batch_words, torch.Tensor):
+            pin.copy_(batch_words)
+        else:
+            pin.numpy()[:] = batch_words
+        self.batch_dev.copy_(pin, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.ring_ev[slot] = ev
+        self._enqueue()
+
+    def step_resident(self):
+        """Step on whatever batch_dev currently holds (inputs already in HBM)."""
+        self._enqueue()
+
+    def capture(self):
+        """CUDA graph of one step on the resident batch buffer; replay with graph.replay()."""
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):  # warm-up outside capture (lazy module load, smem attributes)
+                self._enqueue()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._enqueue()
+        self.graph = g
+        return g
+
+    def batches(self, exact_lazy=False):
+        """One epoch of batch words from the native sampler (advances Python's `random`)."""
+        if self.sampler is None:
+            self.sampler = NativePairSampler(self.data)
+        s = self.sampler
+        s.pull_state()
+        perm = s.begin_epoch(want_perm=True)
+        td = self.data.training_data
+        td[:] = [td[k] for k in perm]
+        if exact_lazy:
+            s.push_state()
+            buf = np.empty(self.words, dtype=np.int32)
+            while True:
+                s.pull_state()
+                b = s.next_batch(self.B, self.B, buf)
+                s.push_state()
+                if b == 0:
+                    return
+                yield buf
+        else:
+            allb = s.epoch(self.B, self.B)
+            s.push_state()
+            for k in range(allb.shape[0]):
+                yield allb[k]
+
+    # ---- inference ---------------------------------------------------------------------
+    def forward_clean(self):
+        """no_grad clean forward -> (user_emb, item_emb), e.g. XSimGCL.py:40-41."""
+        if self.model_name == "MF":
+            out = self.params.clone()
+        else:
+            include_ego = self.model_name in ("LightGCN", "SGL")
+            out, _ = ops.encoder_forward(self.adj, self.params, self.L, include_ego)
+        return out[: self.U], out[self.U:]

@@ -1,0 +1,101 @@
+"""Drop-in for util/sampler.py:5-28 (next_batch_pairwise) on the native sampler.
+
+Bit-exact with the reference given the same `random` state: the MT19937 state is pulled
+from random.getstate() before every native call and pushed back afterwards, so the global
+stream advances exactly as with the Python implementation; data.training_data is permuted
+in place like random.shuffle would.
+"""
+import ctypes as C
+import random
+
+import numpy as np
+
+from .. import _lib
+
+
+class NativePairSampler:
+    """Owns a srb_sampler for one Interaction object."""
+
+    def __init__(self, data):
+        lib = _lib.load()
+        pu = np.ascontiguousarray(data.pair_users if hasattr(data, "pair_users") else [data.user[p[0]] for p in data.training_data], dtype=np.int32)
+        pi = np.ascontiguousarray(data.pair_items if hasattr(data, "pair_items") else [data.item[p[1]] for p in data.training_data], dtype=np.int32)
+        self._lib = lib
+        self.n_pairs = len(pu)
+        self.handle = lib.srb_sampler_create(pu.ctypes.data_as(_lib.c_i32p), pi.ctypes.data_as(_lib.c_i32p), self.n_pairs,
+                                             int(data.user_num), int(data.item_num))
+        if not self.handle:
+            raise _lib.SrbError("srb_sampler_create failed: " + _lib.last_error())
+        self._state = (C.c_uint32 * 625)()
+
+    def __del__(self):
+        if getattr(self, "handle", None):
+            self._lib.srb_sampler_destroy(self.handle)
+            self.handle = None
+
+    def pull_state(self):
+        st = random.getstate()
+        self._gauss = st[2]
+        self._state[:] = st[1]
+        _lib.check(self._lib.srb_sampler_set_state(self.handle, self._state), "srb_sampler_set_state")
+
+    def push_state(self):
+        _lib.check(self._lib.srb_sampler_get_state(self.handle, self._state), "srb_sampler_get_state")
+        random.setstate((3, tuple(self._state), self._gauss))
+
+    def begin_epoch(self, want_perm=True):
+        perm = np.empty(self.n_pairs, dtype=np.int64) if want_perm else None
+        ptr = perm.ctypes.data_as(_lib.c_i64p) if want_perm else None
+        _lib.check(self._lib.srb_sampler_begin_epoch(self.handle, ptr), "srb_sampler_begin_epoch")
+        return perm
+
+    def next_batch_negs(self, batch_size, n_negs, u, i, j):
+        b = self._lib.srb_sampler_next_batch_negs(self.handle, batch_size, n_negs, u.ctypes.data_as(_lib.c_i32p),
+                                                  i.ctypes.data_as(_lib.c_i32p), j.ctypes.data_as(_lib.c_i32p))
+        if b < 0:
+            _lib.check(b, "srb_sampler_next_batch_negs")
+        return b
+
+    def next_batch(self, batch_size, batch_cap, out):
+        """Fixed layout (header + u,i,j,uniq_u,uniq_i) into the int32 array `out`."""
+        b = self._lib.srb_sampler_next_batch(self.handle, batch_size, batch_cap, out.ctypes.data_as(_lib.c_i32p))
+        if b < 0:
+            _lib.check(b, "srb_sampler_next_batch")
+        return b
+
+    def epoch(self, batch_size, batch_cap):
+        """All batches of one epoch (after begin_epoch): int32 array [n_batches, words]."""
+        words = _lib.BATCH_HEADER + 5 * batch_cap
+        nb = (self.n_pairs + batch_size - 1) // batch_size
+        out = np.empty((nb, words), dtype=np.int32)
+        got = self._lib.srb_sampler_epoch(self.handle, batch_size, batch_cap, out.ctypes.data_as(_lib.c_i32p), out.size)
+        if got < 0:
+            _lib.check(int(got), "srb_sampler_epoch")
+        return out[:got]
+
+
+def _sampler_for(data):
+    s = getattr(data, "_srb_sampler", None)
+    if s is None or s.n_pairs != len(data.training_data):
+        s = NativePairSampler(data)
+        data._srb_sampler = s
+    return s
+
+
+def next_batch_pairwise(data, batch_size, n_negs=1):
+    s = _sampler_for(data)
+    s.pull_state()
+    perm = s.begin_epoch(want_perm=True)
+    s.push_state()
+    td = data.training_data
+    td[:] = [td[k] for k in perm]  # the in-place shuffle side effect (sampler.py:7)
+    u = np.empty(batch_size, dtype=np.int32)
+    i = np.empty(batch_size, dtype=np.int32)
+    j = np.empty(batch_size * n_negs, dtype=np.int32)
+    while True:
+        s.pull_state()
+        b = s.next_batch_negs(batch_size, n_negs, u, i, j)
+        s.push_state()
+        if b == 0:
+            return
+        yield u[:b].tolist(), i[:b].tolist(), j[: b * n_negs].tolist()
