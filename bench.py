@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on BASELINE.json's config, on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+metric  : XSimGCL yelp2018 train steps/sec (+ full-catalog rank items/sec as `rank`)
+workload: configs[2]/[1] of BASELINE.json -- XSimGCL, yelp2018 shape (31 668 x 38 048 x 1 237 259,
+          synthetic power-law graph of that shape), 3 layers, d=64, B=2048, tau=0.2, lambda=0.2,
+          eps=0.2, l*=1, lr=1e-3, reg=1e-4, fp32.
+A step  = one pass of the hot path over one batch: propagate (3 SpMM) -> gather + BPR + L2 ->
+          InfoNCE -> Horner backward (3 SpMM) -> Adam, on in-kernel Philox noise.
+value   = steps/s with the batch indices already resident in HBM (a device pool of pre-sampled
+          batches), CUDA-graph replay, CUDA-event timing, max over ranks.
+e2e     = the same metric through the public API with HOST buffers: native sampler ->
+          TrainEngine.step(words) (pinned H2D copy) -> loss read back (D2H) every step.
+--impl reference times the reference's CPU PyTorch path (oracle/torch_port.py, the op-for-op
+port pinned against the reference) on the host cores; rank 0 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(model="XSimGCL", shape="yelp2018", d=64, L=3, B=2048, tau=0.2, lam=0.2, eps=0.2, l_star=1, lr=1e-3, reg=1e-4)
+METRIC = "XSimGCL yelp2018 train steps/sec"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        with open(self.path) as f:
+            for line in f:
+                parts = [x.strip() for x in line.split(",")]
+                if len(parts) < 9:
+                    continue
+                try:
+                    sm.append(float(parts[1]))
+                    mx.append(float(parts[2]))
+                except ValueError:
+                    continue
+                for nm, val in zip(names, parts[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+        os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def spmm_bytes(n, nnz, d):
+    """compulsory bytes of one SpMM = read CSR once + read X once + write Y once."""
+    return 8 * nnz + 4 * (n + 1) + 8 * n * d
+
+
+def build_data(seed=0):
+    from selfrec_b200 import synth
+    return synth.make_interaction(CFG["shape"], seed=seed)
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU PyTorch path (port), host cores
+# ------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import random
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle
+    import torch_port
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    data = build_data()
+    random.seed(0)
+    torch.manual_seed(0)
+    m = torch_port.XSimGCLCpu(data.norm_adj.tocsr(), data.user_num, data.item_num, CFG["d"], CFG["L"], CFG["eps"], CFG["tau"],
+                              CFG["lam"], CFG["l_star"], CFG["lr"], CFG["reg"])
+    rp, ri = data.rated_csr()
+    rated = [set(ri[rp[u]:rp[u + 1]].tolist()) for u in range(data.user_num)]
+    perm = np.random.default_rng(0).permutation(len(data.pair_users))
+    pu, pi = data.pair_users[perm], data.pair_items[perm]
+    ptr = 0
+
+    def one():
+        nonlocal ptr
+        u, i, j, ptr = torch_port.sample_batch(pu, pi, ptr, CFG["B"], data.item_num, rated)
+        m.step(u, i, j)
+
+    for _ in range(args.warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one()
+    dt = time.perf_counter() - t0
+    val = args.steps / dt
+    # rank metric on a bounded sample of users
+    ue, ie = m.ue.detach().numpy(), m.ie.detach().numpy()
+    sample = np.arange(0, data.user_num, max(1, data.user_num // 1000))[:1000]
+    t0 = time.perf_counter()
+    torch_port.rank_users(ue, ie, sample, rp, ri, 20, oracle.find_k_largest)
+    rdt = time.perf_counter() - t0
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "XSimGCL yelp2018-shape 31668x38048x1237259, L=3 d=64 B=2048 tau=0.2 lambda=0.2 eps=0.2 l*=1",
+                   "note": "reference CPU PyTorch path (op-for-op port, oracle/torch_port.py) incl. Python sampler"},
+        "cpu_baseline": {"value": val, "unit": "steps/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} full train steps after {args.warmup} warm-up"},
+        "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "rank": {"value": len(sample) * data.item_num / rdt, "unit": "items/s", "sample": f"{len(sample)} of {data.user_num} users"},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import random
+    import torch
+    import torch.distributed as dist
+    from selfrec_b200 import _lib, build, ops
+    build.build()
+    lib = _lib.require_device()  # fails loudly without a GPU / without the library
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    from selfrec_b200.engine import TrainEngine
+
+    data = build_data()
+    random.seed(1234 + rank)
+    torch.manual_seed(1234)
+    eng = TrainEngine("XSimGCL", data, CFG["d"], CFG["L"], CFG["B"], CFG["lr"], CFG["reg"], eps=CFG["eps"], tau=CFG["tau"],
+                      cl_rate=CFG["lam"], layer_cl=CFG["l_star"], device=dev, philox_seed=2026 + rank)
+    # device-resident pool of pre-sampled batches (inputs in HBM before the timed region)
+    P = 64
+    pool_host = np.stack([w.copy() for _, w in zip(range(P), eng.batches())])
+    pool = torch.from_numpy(pool_host).to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    # launches per step (eager), then capture
+    eng.batch_dev.copy_(pool[0])
+    torch.cuda.synchronize()
+    l0 = _lib.launch_count()
+    eng.step_resident()
+    torch.cuda.synchronize()
+    launches_per_step = _lib.launch_count() - l0
+    graph = eng.capture()
+
+    def resident_step(k):
+        eng.batch_dev.copy_(pool[k % P], non_blocking=True)  # D2D, 41 KB
+        graph.replay()
+
+    for k in range(max(args.warmup, 3)):
+        resident_step(k)
+    torch.cuda.synchronize()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for k in range(args.steps):
+        resident_step(k)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * args.steps / (ms * 1e-3)  # weak scaling: every rank trains its own replica shard of batches
+
+    # same loop with an L2 flush between iterations, per-step events (extra evidence)
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)
+    per = []
+    for k in range(min(args.steps, 20)):
+        flush.fill_(float(k))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        resident_step(k)
+        e1.record()
+        torch.cuda.synchronize()
+        per.append(e0.elapsed_time(e1))
+    ms_flushed = float(np.mean(per))
+    del flush
+
+    # ---- e2e: public API, host buffers, H2D + D2H every step -------------------------------
+    gen = eng.batches()
+    for _ in range(max(args.warmup, 3)):
+        eng.step(next(gen))
+        eng.losses.cpu()
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.step(next(gen))
+        loss_host = eng.losses.cpu()  # D2H read of the step's result (syncs)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = world * args.steps / float(te.item())
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel (SpMM), live CUDA-event timing ---------------------
+    N, nnzA = eng.N, eng.adj._nnz()
+    x = torch.randn(N, CFG["d"], device=dev)
+    y = torch.empty_like(x)
+    for _ in range(3):
+        ops._spmm_raw(eng.adj, x, y)
+    R = 50
+    ev0.record()
+    for _ in range(R):
+        ops._spmm_raw(eng.adj, x, y)
+        ops._spmm_raw(eng.adj, y, x)
+    ev1.record()
+    torch.cuda.synchronize()
+    spmm_ms = ev0.elapsed_time(ev1) / (2 * R)
+    alg = spmm_bytes(N, nnzA, CFG["d"])
+    peak, peak_src = peaks()
+    achieved = alg / (spmm_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "spmm_traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    step_bytes = 2 * CFG["L"] * alg + 28 * N * CFG["d"]
+
+    # ---- rank metric ---------------------------------------------------------------------
+    ue, ie = eng.forward_clean()
+    rp, ri = data.rated_csr()
+    users = torch.arange(eng.U, device=dev, dtype=torch.int32)
+    rpd, rid = torch.from_numpy(rp).to(dev), torch.from_numpy(ri).to(dev)
+    ops.score_topk(ue, ie, users, rpd, rid, 20)
+    ev0.record()
+    for _ in range(3):
+        ops.score_topk(ue, ie, users, rpd, rid, 20)
+    ev1.record()
+    torch.cuda.synchronize()
+    rank_ms = ev0.elapsed_time(ev1) / 3
+    rank_val = eng.U * eng.I / (rank_ms * 1e-3)
+
+    # ---- CPU baseline: bounded sample of the same workload on the host cores ------------------
+    cpu = cpu_baseline(data, args)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "XSimGCL yelp2018-shape 31668x38048x1237259, L=3 d=64 B=2048 tau=0.2 lambda=0.2 eps=0.2 l*=1",
+                   "parallelism": f"dp{world} (independent replicas)" if world > 1 else "single GPU",
+                   "l2": "no flush: per-step working set ~180 MB > 126 MB L2 (see value_l2_flushed)",
+                   "inputs": f"{P} pre-sampled batches resident in HBM, CUDA-graph replay"},
+        "clocks": clk,
+        "e2e": {"value": e2e_val, "unit": "steps/s", "h2d_bytes_per_step": int(eng.words * 4), "d2h_bytes_per_step": 16,
+                "note": "native sampler + pinned H2D + fused step + loss D2H each step"},
+        "gpu_launches": int(launches_per_step * args.steps),
+        "launches_per_step": int(launches_per_step),
+        "value_l2_flushed": 1e3 / ms_flushed, "ms_per_step_l2_flushed": ms_flushed,
+        "roofline": {"bound": "hbm", "kernel": "spmm_csr_kernel<64>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "ms_per_launch": spmm_ms,
+                     "algorithmic_bytes_per_launch": alg,
+                     "step": {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (ms / args.steps * 1e-3) / 1e9,
+                              "frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak}},
+        "rank": {"metric": "full-catalog rank items/sec", "value": rank_val, "unit": "items/s", "ms": rank_ms,
+                 "users": eng.U, "items": eng.I, "k": 20, "impl": "cuda-core fp32"},
+        "cpu_baseline": cpu,
+        "loss": [float(v) for v in loss_host.tolist()],
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(data, args):
+    """The reference's CPU path (port) on a bounded sample: a few train steps on the host cores."""
+    import random
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch_port
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    random.seed(0)
+    m = torch_port.XSimGCLCpu(data.norm_adj.tocsr(), data.user_num, data.item_num, CFG["d"], CFG["L"], CFG["eps"], CFG["tau"],
+                              CFG["lam"], CFG["l_star"], CFG["lr"], CFG["reg"])
+    rp, ri = data.rated_csr()
+    rated = [set(ri[rp[u]:rp[u + 1]].tolist()) for u in range(data.user_num)]
+    ptr = 0
+    n = 0
+    t0 = None
+    budget = 15.0
+    while True:
+        u, i, j, ptr = torch_port.sample_batch(data.pair_users, data.pair_items, ptr, CFG["B"], data.item_num, rated)
+        m.step(u, i, j)
+        if t0 is None:
+            t0 = time.perf_counter()  # first step = warm-up
+            continue
+        n += 1
+        if time.perf_counter() - t0 > budget or n >= 20:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "steps/s", "cores": cores, "kind": "port",
+            "sample": f"{n} full XSimGCL train steps (oracle/torch_port.py, torch CPU, Python sampler) after 1 warm-up"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if args.steps > 20:
+            args.steps = 20  # bounded sample: ~1 s per CPU step
+        args.warmup = min(args.warmup, 2)
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -156,3 +156,22 @@ def test_ranking_matches_reference_test(orc, golden):
     names = g["item_names"][ids]
     assert np.array_equal(names, r["items"])  # bit-exact top-k item ids
     np.testing.assert_allclose(sc, r["scores"], rtol=2e-5, atol=1e-7)
+
+
+def test_torch_cpu_port_matches_reference(golden):
+    """oracle/torch_port.py (the CPU baseline / reference arm of bench.py) reproduces the
+    reference's own XSimGCL train() parameters step for step."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import torch
+    import torch_port
+    g, U, I, norm = _graph(golden)
+    fx = golden("train_XSimGCL.npz")
+    m = torch_port.XSimGCLCpu(norm, U, I, 64, 3, 0.2, 0.2, 0.2, 1, 0.001, 0.0001, fx["init_user"], fx["init_item"])
+    tags, vals = list(fx["loss_tags"]), list(fx["loss_vals"])
+    for k in range(int(fx["n_steps"])):
+        nz = [torch.from_numpy(fx["noise"][k * 3 + l]) for l in range(3)]
+        rec, l2, cl = m.step(fx[f"b{k}_u"].tolist(), fx[f"b{k}_i"].tolist(), fx[f"b{k}_j"].tolist(), nz)
+        assert abs(rec - vals[k * 4]) <= 1e-6 * abs(rec)
+        got = torch.cat([m.ue, m.ie]).detach().numpy()
+        np.testing.assert_allclose(got, fx[f"params_after_{k}"], rtol=1e-6, atol=1e-8)
