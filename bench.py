@@ -186,6 +186,19 @@ def run_ours(args, rank, world, local_rank):
         if world > 1:
             dist.barrier()
 
+    if args.profile:
+        # ncu mode: eager launches only (every kernel individually visible), no baselines
+        gen = eng.batches()
+        for _ in range(args.warmup + args.steps):
+            eng.step(next(gen))
+        ue, ie = eng.forward_clean()
+        rp, ri = data.rated_csr()
+        ops.score_topk(ue, ie, torch.arange(eng.U, device=dev, dtype=torch.int32), torch.from_numpy(rp).to(dev),
+                       torch.from_numpy(ri).to(dev), 20)
+        torch.cuda.synchronize()
+        print(json.dumps({"profile_mode": True, "launches": _lib.launch_count()}))
+        return
+
     # launches per step (eager), then capture
     eng.batch_dev.copy_(pool[0])
     torch.cuda.synchronize()
@@ -361,6 +374,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--profile", action="store_true", help="eager steps only, for ncu (never a bench value)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -78,7 +78,8 @@ typedef struct srb_spmm_desc {
   float* adam_m;
   float* adam_v;
   const float* adam_scalars; /* device: {step_size, bias_correction2_sqrt} */
-  float beta1, beta2, adam_eps;
+  double beta1, beta2;       /* doubles: 1 - beta is rounded to fp32 from the double, like torch */
+  float adam_eps;
 } srb_spmm_desc;
 
 int srb_spmm_csr(const srb_spmm_desc* desc, void* stream);
@@ -221,7 +222,7 @@ int srb_scatter_add_rows(float* dst, int32_t d, const float* src, const int32_t*
 int srb_adam_prepare(int32_t* step_dev, float* scalars_dev, double lr, double beta1,
                      double beta2, void* stream);
 int srb_adam_step(float* p, float* m, float* v, const float* g, int64_t n,
-                  const float* scalars_dev, float beta1, float beta2, float eps,
+                  const float* scalars_dev, double beta1, double beta2, float eps,
                   void* stream);
 
 /* ---------------------------------------------------------------------------------------

@@ -30,7 +30,7 @@ class SpmmDesc(C.Structure):
         ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64), ("philox_step_dev", VP),
         ("sum_in", VP), ("sum_out", VP), ("sum_scale", C.c_float),
         ("adam_p", VP), ("adam_m", VP), ("adam_v", VP), ("adam_scalars", VP),
-        ("beta1", C.c_float), ("beta2", C.c_float), ("adam_eps", C.c_float),
+        ("beta1", C.c_double), ("beta2", C.c_double), ("adam_eps", C.c_float),
     ]
 
 
@@ -116,7 +116,7 @@ SYMBOLS = {
     "srb_l2_reg_bwd": (C.c_int, [C.c_int32, C.POINTER(VP), C.POINTER(VP), c_i64p, c_i32p, C.c_float, VP, VP, VP]),
     "srb_scatter_add_rows": (C.c_int, [VP, C.c_int32, VP, VP, C.c_int32, VP, C.c_int32, C.c_float, VP]),
     "srb_adam_prepare": (C.c_int, [VP, VP, C.c_double, C.c_double, C.c_double, VP]),
-    "srb_adam_step": (C.c_int, [VP, VP, VP, VP, C.c_int64, VP, C.c_float, C.c_float, C.c_float, VP]),
+    "srb_adam_step": (C.c_int, [VP, VP, VP, VP, C.c_int64, VP, C.c_double, C.c_double, C.c_float, VP]),
     "srb_topk_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "srb_score_topk": (C.c_int, [C.POINTER(TopkDesc), VP]),
     "srb_score_rows": (C.c_int, [VP, VP, C.c_int32, VP, C.c_int32, C.c_int32, VP, VP]),

@@ -251,9 +251,8 @@ __global__ void adam_prepare_kernel(int32_t* step, float* scalars, double lr, do
 
 __global__ void __launch_bounds__(256) adam_step_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
                                                         const float* __restrict__ g, long long n4, long long n,
-                                                        const float* __restrict__ scal, float b1, float b2, float eps) {
+                                                        const float* __restrict__ scal, float w1, float b2, float w2, float eps) {
   const float step_size = scal[0], bc2_sqrt = scal[1];
-  const float w1 = 1.f - b1, w2 = 1.f - b2;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 pp = reinterpret_cast<float4*>(p)[i], mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
@@ -343,8 +342,8 @@ extern "C" int srb_adam_prepare(int32_t* step_dev, float* scalars_dev, double lr
   return srb::post_launch("adam_prepare_kernel");
 }
 
-extern "C" int srb_adam_step(float* p, float* m, float* v, const float* g, int64_t n, const float* scalars_dev, float beta1,
-                             float beta2, float eps, void* stream) {
+extern "C" int srb_adam_step(float* p, float* m, float* v, const float* g, int64_t n, const float* scalars_dev, double beta1,
+                             double beta2, float eps, void* stream) {
   SRB_REQUIRE(p && m && v && g && scalars_dev, "adam_step: null pointer");
   SRB_REQUIRE(n >= 0, "adam_step: negative n");
   if (n == 0) return SRB_OK;
@@ -353,7 +352,8 @@ extern "C" int srb_adam_step(float* p, float* m, float* v, const float* g, int64
   const long long cap = (long long)srb::sm_count() * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  srb::adam_step_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p, m, v, g, n4, n, scalars_dev, beta1, beta2, eps);
+  srb::adam_step_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p, m, v, g, n4, n, scalars_dev, (float)(1.0 - beta1), (float)beta2,
+                                                                        (float)(1.0 - beta2), eps);
   return srb::post_launch("adam_step_kernel");
 }
 

@@ -139,8 +139,8 @@ static int spmm_simple(const srb_step_desc* s, const srb_graph_csr* g, const flo
     p.adam_m = s->adam_m;
     p.adam_v = s->adam_v;
     p.adam_scalars = s->scalars;
-    p.beta1 = (float)s->beta1;
-    p.beta2 = (float)s->beta2;
+    p.beta1 = s->beta1;
+    p.beta2 = s->beta2;
     p.adam_eps = s->adam_eps;
   }
   return srb_spmm_csr(&p, st);
@@ -357,8 +357,8 @@ extern "C" int srb_train_step(const srb_step_desc* s, void* stream) {
     sg.s[1] = seg(w.g_emb + plane, i_idx, b_dev, B, U, 1.f);
     sg.s[2] = seg(w.g_emb + 2 * plane, j_idx, b_dev, B, U, 1.f);
     SRB_TRY(scatter_segments(w.acc0, d, sg, st));
-    return srb_adam_step(s->params, s->adam_m, s->adam_v, w.acc0, (int64_t)N * d, s->scalars, (float)s->beta1,
-                         (float)s->beta2, s->adam_eps, stream);
+    return srb_adam_step(s->params, s->adam_m, s->adam_v, w.acc0, (int64_t)N * d, s->scalars, s->beta1, s->beta2, s->adam_eps,
+                         stream);
   }
   const float cm = 1.f / (float)((s->model == SRB_MODEL_LIGHTGCN || s->model == SRB_MODEL_SGL) ? L + 1 : L);
   bool gd_live = false;

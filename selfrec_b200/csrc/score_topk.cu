@@ -31,6 +31,8 @@ struct TopkArgs {
   int32_t k;
   int32_t* out_ids;
   float* out_scores;
+  const int32_t* q_map;    // optional: output row of query q (fallback path of impl 2)
+  const int32_t* n_q_dev;  // optional: device-side query count (<= n_q)
 };
 
 template <int D>
@@ -41,12 +43,14 @@ __global__ void __launch_bounds__(256) score_topk_kernel(const TopkArgs a) {
   const int lane = threadIdx.x & 31;
   const int ty = threadIdx.x >> 5;  // warp id: users ty*4 .. ty*4+3 of the CTA tile
   const int q0 = blockIdx.x * TK_TM;
+  const int n_q = a.n_q_dev ? min(*a.n_q_dev, a.n_q) : a.n_q;
+  if (q0 >= n_q) return;
 
   // user tile (gathered by id), transposed to k-major
   for (int e = threadIdx.x; e < TK_TM * (D / 4); e += blockDim.x) {
     const int u = e % TK_TM, k4 = e / TK_TM;
     float4 v = f4_zero();
-    if (q0 + u < a.n_q) v = ldg4(a.user_emb + (size_t)a.users[q0 + u] * D + k4 * 4);
+    if (q0 + u < n_q) v = ldg4(a.user_emb + (size_t)a.users[q0 + u] * D + k4 * 4);
     Us[k4 * 4 + 0][u] = v.x;
     Us[k4 * 4 + 1][u] = v.y;
     Us[k4 * 4 + 2][u] = v.z;
@@ -62,7 +66,7 @@ __global__ void __launch_bounds__(256) score_topk_kernel(const TopkArgs a) {
     ls[r] = -INFINITY;
     li[r] = -1;
     const int q = q0 + ty * 4 + r;
-    if (q < a.n_q && a.rated_ptr) {
+    if (q < n_q && a.rated_ptr) {
       const int u = a.users[q];
       cur[r] = a.rated_ptr[u];
       cend[r] = a.rated_ptr[u + 1];
@@ -152,9 +156,10 @@ __global__ void __launch_bounds__(256) score_topk_kernel(const TopkArgs a) {
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
     const int q = q0 + ty * 4 + r;
-    if (q < a.n_q && lane < K) {
-      a.out_ids[(size_t)q * K + lane] = li[r];
-      a.out_scores[(size_t)q * K + lane] = ls[r];
+    if (q < n_q && lane < K) {
+      const size_t orow = a.q_map ? (size_t)a.q_map[q] : (size_t)q;
+      a.out_ids[orow * K + lane] = li[r];
+      a.out_scores[orow * K + lane] = ls[r];
     }
   }
 }
@@ -234,17 +239,39 @@ static int launch_topk(const TopkArgs& a, cudaStream_t st) {
   return post_launch("score_topk_kernel");
 }
 
+// exact re-run of the users impl 2 could not certify (device-side list and count)
+int score_topk_fallback(const srb_topk_desc* d, const int32_t* fb_users, const int32_t* fb_rows, const int32_t* fb_count,
+                        cudaStream_t st) {
+  TopkArgs a;
+  a.user_emb = d->user_emb;
+  a.item_emb = d->item_emb;
+  a.n_items = d->n_items;
+  a.users = fb_users;
+  a.n_q = d->n_q;
+  a.rated_ptr = d->rated_ptr;
+  a.rated_idx = d->rated_idx;
+  a.k = d->k;
+  a.out_ids = d->out_ids;
+  a.out_scores = d->out_scores;
+  a.q_map = fb_rows;
+  a.n_q_dev = fb_count;
+  return launch_topk<64>(a, st);
+}
+
 }  // namespace srb
 
 extern "C" int srb_score_topk(const srb_topk_desc* d, void* stream) {
   SRB_REQUIRE(d != nullptr, "topk: null desc");
+  SRB_REQUIRE(d->n_q >= 0, "topk: negative n_q");
+  if (d->n_q == 0) return SRB_OK;  // empty query list: nothing to launch (pointers may be null)
   SRB_REQUIRE(d->user_emb && d->item_emb && d->users && d->out_ids && d->out_scores, "topk: null pointer");
   SRB_REQUIRE((d->rated_ptr == nullptr) == (d->rated_idx == nullptr), "topk: rated_ptr/rated_idx must both be set or both null");
   SRB_REQUIRE(d->k >= 1 && d->k <= 32, "topk: k=%d unsupported (1..32)", d->k);
   SRB_REQUIRE(d->n_items >= 1 && d->n_q >= 0, "topk: bad shape");
   SRB_REQUIRE(d->impl >= 0 && d->impl <= 2, "topk: bad impl");
   if (d->n_q == 0) return SRB_OK;
-  if (d->impl == 2) return srb::score_topk_tc(d, (cudaStream_t)stream);
+  if (d->impl == 2 || (d->impl == 0 && d->d == 64 && d->workspace != nullptr && d->n_items >= 1024))
+    return srb::score_topk_tc(d, (cudaStream_t)stream);
   srb::TopkArgs a;
   a.user_emb = d->user_emb;
   a.item_emb = d->item_emb;
@@ -256,6 +283,8 @@ extern "C" int srb_score_topk(const srb_topk_desc* d, void* stream) {
   a.k = d->k;
   a.out_ids = d->out_ids;
   a.out_scores = d->out_scores;
+  a.q_map = nullptr;
+  a.n_q_dev = nullptr;
   switch (d->d) {
     case 32: return srb::launch_topk<32>(a, (cudaStream_t)stream);
     case 64: return srb::launch_topk<64>(a, (cudaStream_t)stream);

@@ -4,12 +4,8 @@
 // SimGCL.py:85, XSimGCL.py:88, SGL.py:104-108 -- plus the elementwise tail of the encoders
 // (XSimGCL.py:90-96) and, for the last backward product, torch.optim.Adam.step.
 //
-// Mapping: one warp per output row.  A row vector of D floats is held as one float4 per
-// lane by LPR = D/4 lanes; the 32/LPR lane groups of the warp walk alternating non-zeros
-// and are combined with xor-shuffles at the end.  (col, val) pairs are fetched 32 at a
-// time with coalesced loads and broadcast by shuffle; the X-row gathers are 128-bit
-// loads, UNROLL x (32/LPR) rows of X in flight per warp.  HBM/L2-bound integer+fp32 work:
-// no tensor cores here by design.
+// HBM/L2-bound integer + fp32 work: no tensor cores here by design (see the kernel comment
+// for the lane mapping).
 #include "common.cuh"
 
 namespace srb {
@@ -37,116 +33,144 @@ struct SpmmArgs {
   float* am;
   float* av;
   const float* ascal;
-  float b1, b2, aeps;
+  float b2, w1, w2, aeps;  // beta2, 1 - beta1, 1 - beta2 (rounded from double like torch's Python floats)
   int32_t world;
   int32_t row_begin;
   float* peer[8];
 };
 
+// Mapping: a row vector of D floats lives on LPR = D/8 lanes (two float4 per lane: columns
+// [4*gl, 4*gl+4) and [D/2 + 4*gl, ...)), so a warp works on RPW = 32/LPR rows at once (4 rows for
+// d = 64).  Rows are taken in `row_order` (degree-descending), which keeps the RPW rows of a warp
+// equally long.  Each lane group loads LPR consecutive (col, val) pairs with one coalesced load,
+// then walks them with group-wide shuffles; every X-row gather is two 128-bit ld.global.nc per
+// lane (LPR lanes x 16 B = one contiguous half row), all gathers of a batch are issued before the
+// FMAs so 2*LPR independent loads per lane are in flight.  ~4 warp instructions per non-zero
+// (the first version needed 18 and was issue-bound at 20 % of L2 throughput).
 template <int D>
 __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmArgs a) {
-  constexpr int LPR = D / 4;    // lanes holding one row vector
-  constexpr int NZP = 32 / LPR; // non-zeros processed concurrently by the warp
-  constexpr int UNROLL = 4;
+  constexpr int LPR = D / 8;     // lanes per row
+  constexpr int RPW = 32 / LPR;  // rows per warp
+  constexpr int HALF = D / 2;
   const int lane = threadIdx.x & 31;
-  const int sub = lane / LPR;
-  const int cl = lane % LPR;
+  const int grp = lane / LPR;
+  const int gl = lane % LPR;
   const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int n_quads = (a.n_rows + RPW - 1) / RPW;
 
-  for (int w = warp0; w < a.n_rows; w += nwarps) {
-    const int row = a.row_order ? __ldg(a.row_order + w) : w;
-    const int beg = __ldg(a.rowptr + row);
-    const int end = __ldg(a.rowptr + row + 1);
-    float4 acc = f4_zero();
-    for (int base = beg; base < end; base += 32) {
-      const int idx = base + lane;
-      int c = 0;
+  for (int wq = warp0; wq < n_quads; wq += nwarps) {
+    const int ridx = wq * RPW + grp;
+    const bool valid = ridx < a.n_rows;
+    int row = 0, p = 0, end = 0;
+    if (valid) {
+      row = a.row_order ? __ldg(a.row_order + ridx) : ridx;
+      p = __ldg(a.rowptr + row);
+      end = __ldg(a.rowptr + row + 1);
+    }
+    float4 acc0 = f4_zero(), acc1 = f4_zero();
+    while (__any_sync(SRB_FULL_MASK, p < end)) {
+      const int idx = p + gl;
+      int c = 0;  // padding slots gather row 0 with weight 0 (an L1 hit) instead of branching
       float v = 0.f;
       if (idx < end) {
         c = __ldg(a.colidx + idx);
         v = __ldg(a.vals + idx);
       }
-      const int cnt = min(32, end - base);
-      for (int j = 0; j < cnt; j += NZP * UNROLL) {
-        int cc[UNROLL];
-        float vv[UNROLL];
+      constexpr int SB = LPR < 4 ? LPR : 4;  // sub-batch: 2*SB independent 128-bit gathers per lane in flight
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-          const int jj = j + u * NZP + sub;
-          cc[u] = __shfl_sync(SRB_FULL_MASK, c, jj & 31);
-          vv[u] = __shfl_sync(SRB_FULL_MASK, v, jj & 31);
-          if (jj >= cnt) vv[u] = 0.f, cc[u] = -1;
+      for (int j0 = 0; j0 < LPR; j0 += SB) {
+        if (j0 > 0 && !__any_sync(SRB_FULL_MASK, p + j0 < end)) break;
+        float vv[SB];
+        float4 x0[SB], x1[SB];
+#pragma unroll
+        for (int j = 0; j < SB; ++j) {
+          const int cc = __shfl_sync(SRB_FULL_MASK, c, j0 + j, LPR);
+          vv[j] = __shfl_sync(SRB_FULL_MASK, v, j0 + j, LPR);
+          const float* xr = a.X + (size_t)cc * D + gl * 4;
+          x0[j] = ldg4(xr);
+          x1[j] = ldg4(xr + HALF);
         }
-        float4 x[UNROLL];
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u)
-          x[u] = (cc[u] >= 0) ? ldg4(a.X + (size_t)cc[u] * D + cl * 4) : f4_zero();
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u) acc = f4_fma(vv[u], x[u], acc);
+        for (int j = 0; j < SB; ++j) {
+          acc0 = f4_fma(vv[j], x0[j], acc0);
+          acc1 = f4_fma(vv[j], x1[j], acc1);
+        }
       }
+      p += LPR;
     }
-#pragma unroll
-    for (int o = LPR; o < 32; o <<= 1) {
-      acc.x += __shfl_xor_sync(SRB_FULL_MASK, acc.x, o);
-      acc.y += __shfl_xor_sync(SRB_FULL_MASK, acc.y, o);
-      acc.z += __shfl_xor_sync(SRB_FULL_MASK, acc.z, o);
-      acc.w += __shfl_xor_sync(SRB_FULL_MASK, acc.w, o);
-    }
-    // ---- epilogue: every lane group holds the full row; group 0 stores ----
-    const size_t off = (size_t)row * D + cl * 4;
-    float4 y = acc;
-    if (a.extra) {
-      const float4 e = *reinterpret_cast<const float4*>(a.extra + off);
-      y = f4_fma(a.extra_scale, e, y);
+    // ---- epilogue (per lane group = per row) ----
+    const size_t off = (size_t)row * D + gl * 4;
+    float4 y0 = acc0, y1 = acc1;
+    if (a.extra && valid) {
+      y0 = f4_fma(a.extra_scale, *reinterpret_cast<const float4*>(a.extra + off), y0);
+      y1 = f4_fma(a.extra_scale, *reinterpret_cast<const float4*>(a.extra + off + HALF), y1);
     }
     if (a.noise_mode) {
-      float4 nz;
+      float4 n0 = f4_zero(), n1 = f4_zero();
       if (a.noise_mode == 1) {
-        nz = ldg4(a.noise + off);
+        if (valid) {
+          n0 = ldg4(a.noise + off);
+          n1 = ldg4(a.noise + off + HALF);
+        }
       } else {
         const uint32_t stp = a.pstep ? (uint32_t)*a.pstep : 0u;
-        const uint4 r = philox4x32_10(make_uint4((uint32_t)row, (uint32_t)cl, a.poff.x, a.poff.y ^ stp), a.pkey);
-        nz = make_float4(u32_to_unit(r.x), u32_to_unit(r.y), u32_to_unit(r.z), u32_to_unit(r.w));
+        const uint4 r0 = philox4x32_10(make_uint4((uint32_t)row, (uint32_t)gl, a.poff.x, a.poff.y ^ stp), a.pkey);
+        const uint4 r1 = philox4x32_10(make_uint4((uint32_t)row, (uint32_t)(gl + LPR), a.poff.x, a.poff.y ^ stp), a.pkey);
+        n0 = make_float4(u32_to_unit(r0.x), u32_to_unit(r0.y), u32_to_unit(r0.z), u32_to_unit(r0.w));
+        n1 = make_float4(u32_to_unit(r1.x), u32_to_unit(r1.y), u32_to_unit(r1.z), u32_to_unit(r1.w));
       }
-      float ss = f4_dot(nz, nz);
+      float ss = f4_dot(n0, n0) + f4_dot(n1, n1);
 #pragma unroll
       for (int o = LPR / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(SRB_FULL_MASK, ss, o);
       const float nrm = fmaxf(sqrtf(ss), 1e-12f);  // F.normalize eps
-      y.x += sgnf(y.x) * (nz.x / nrm) * a.eps;
-      y.y += sgnf(y.y) * (nz.y / nrm) * a.eps;
-      y.z += sgnf(y.z) * (nz.z / nrm) * a.eps;
-      y.w += sgnf(y.w) * (nz.w / nrm) * a.eps;
+#define SRB_PERT(Y, N, F) Y.F += sgnf(Y.F) * (N.F / nrm) * a.eps;
+      SRB_PERT(y0, n0, x) SRB_PERT(y0, n0, y) SRB_PERT(y0, n0, z) SRB_PERT(y0, n0, w)
+      SRB_PERT(y1, n1, x) SRB_PERT(y1, n1, y) SRB_PERT(y1, n1, z) SRB_PERT(y1, n1, w)
+#undef SRB_PERT
     }
-    if (sub == 0) {
-      if (a.Y) st4(a.Y + off, y);
-      if (a.world > 0) {
-        const size_t goff = (size_t)(a.row_begin + row) * D + cl * 4;
+    if (!valid) continue;
+    if (a.Y) {
+      st4(a.Y + off, y0);
+      st4(a.Y + off + HALF, y1);
+    }
+    if (a.world > 0) {
+      const size_t goff = (size_t)(a.row_begin + row) * D + gl * 4;
 #pragma unroll 1
-        for (int g = 0; g < a.world; ++g) st4(a.peer[g] + goff, y);
+      for (int g = 0; g < a.world; ++g) {
+        st4(a.peer[g] + goff, y0);
+        st4(a.peer[g] + goff + HALF, y1);
       }
-      if (a.sum_out) {
-        float4 s = y;
-        if (a.sum_in) s = f4_add(s, *reinterpret_cast<const float4*>(a.sum_in + off));
-        st4(a.sum_out + off, f4_scale(a.sum_scale, s));
+    }
+    if (a.sum_out) {
+      float4 s0 = y0, s1 = y1;
+      if (a.sum_in) {
+        s0 = f4_add(s0, *reinterpret_cast<const float4*>(a.sum_in + off));
+        s1 = f4_add(s1, *reinterpret_cast<const float4*>(a.sum_in + off + HALF));
       }
-      if (a.ap) {
-        const float step_size = a.ascal[0];
-        const float bc2_sqrt = a.ascal[1];
-        float4 p = *reinterpret_cast<const float4*>(a.ap + off);
-        float4 m = *reinterpret_cast<const float4*>(a.am + off);
-        float4 v = *reinterpret_cast<const float4*>(a.av + off);
-        const float w1 = 1.f - a.b1, w2 = 1.f - a.b2;
-#define SRB_ADAM1(F)                                         \
-  m.F = m.F + w1 * (y.F - m.F);                              \
-  v.F = v.F * a.b2;                                          \
-  v.F = v.F + (w2 * y.F) * y.F;                              \
-  p.F = p.F - step_size * (m.F / (sqrtf(v.F) / bc2_sqrt + a.aeps));
+      st4(a.sum_out + off, f4_scale(a.sum_scale, s0));
+      st4(a.sum_out + off + HALF, f4_scale(a.sum_scale, s1));
+    }
+    if (a.ap) {
+      const float step_size = a.ascal[0];
+      const float bc2_sqrt = a.ascal[1];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const size_t o2 = off + h * HALF;
+        const float4 g = h ? y1 : y0;
+        float4 p4 = *reinterpret_cast<const float4*>(a.ap + o2);
+        float4 m = *reinterpret_cast<const float4*>(a.am + o2);
+        float4 v4 = *reinterpret_cast<const float4*>(a.av + o2);
+#define SRB_ADAM1(F)                                          \
+  m.F = m.F + a.w1 * (g.F - m.F);                             \
+  v4.F = v4.F * a.b2;                                         \
+  v4.F = v4.F + (a.w2 * g.F) * g.F;                           \
+  p4.F = p4.F - step_size * (m.F / (sqrtf(v4.F) / bc2_sqrt + a.aeps));
         SRB_ADAM1(x) SRB_ADAM1(y) SRB_ADAM1(z) SRB_ADAM1(w)
 #undef SRB_ADAM1
-        st4(a.ap + off, p);
-        st4(a.am + off, m);
-        st4(a.av + off, v);
+        st4(a.ap + o2, p4);
+        st4(a.am + o2, m);
+        st4(a.av + o2, v4);
       }
     }
   }
@@ -155,8 +179,8 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmArgs a) {
 static int launch_spmm(const SpmmArgs& a, int d, cudaStream_t st) {
   if (a.n_rows == 0) return SRB_OK;
   const int threads = 256;
-  const int wpb = threads / 32;
-  long long blocks = ((long long)a.n_rows + wpb - 1) / wpb;
+  const int rows_per_block = (threads / 32) * (32 / (d / 8));
+  long long blocks = ((long long)a.n_rows + rows_per_block - 1) / rows_per_block;
   const long long cap = (long long)sm_count() * 8;  // 8 x 256 threads = full residency
   if (blocks > cap) blocks = cap;
   switch (d) {
@@ -198,8 +222,9 @@ static int fill_args(const srb_spmm_desc* d, SpmmArgs& a) {
   a.am = d->adam_m;
   a.av = d->adam_v;
   a.ascal = d->adam_scalars;
-  a.b1 = d->beta1;
-  a.b2 = d->beta2;
+  a.b2 = (float)d->beta2;
+  a.w1 = (float)(1.0 - d->beta1);
+  a.w2 = (float)(1.0 - d->beta2);
   a.aeps = d->adam_eps;
   a.world = 0;
   a.row_begin = 0;

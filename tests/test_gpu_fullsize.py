@@ -70,12 +70,16 @@ def test_xsimgcl_step_full_size_vs_oracle(yelp, orc, in_tmp_cwd):
     assert abs(los[2] - out["cl"]) <= 1e-4 * abs(out["cl"])
     P, _, _ = orc.adam_step(E0, out["grad"].astype(np.float32), np.zeros_like(E0), np.zeros_like(E0), 1, 1e-3)
     got = eng.params.cpu().numpy()
-    # step 1 of Adam moves a weight by lr * g/(|g| + eps): for |g| ~ eps (1e-8) the quotient is
-    # ill-conditioned, so compare with the embedding tolerance plus lr * 1e-2 absolute
-    np.testing.assert_allclose(got, P, rtol=1e-4, atol=1e-5)
-    g = out["grad"]
-    big = np.abs(g) > 1e-6
-    np.testing.assert_allclose(got[big], P[big], rtol=1e-4, atol=2e-7)
+    # Step 1 of Adam moves a weight by lr * g / (|g| + eps).  Where |g| >> eps = 1e-8 this is +-lr and the
+    # parameters must agree to the embedding tolerance; where |g| ~ eps the quotient amplifies the fp32
+    # rounding of g (relative 2e-4 after three propagation hops) by 1/(|g| + eps): bound that explicitly.
+    g = np.abs(out["grad"])
+    dg = 2e-4 * g + 2e-11
+    tol = 1e-4 * np.abs(P) + 1e-7 + 1e-3 * dg / (g + 1e-8)
+    bad = np.abs(got - P) > tol
+    assert not bad.any(), (int(bad.sum()), float(np.abs(got - P)[bad].max()), float(g[bad].min()), float(g[bad].max()))
+    big = g > 1e-6
+    np.testing.assert_allclose(got[big], P[big], rtol=1e-4, atol=3e-7)
 
 
 def test_full_catalog_ranking_properties(yelp, orc):

