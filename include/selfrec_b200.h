@@ -56,8 +56,10 @@ typedef struct srb_spmm_desc {
   int32_t n_rows;
   int32_t n_cols;
   int32_t d;
-  /* optional processing order of rows (length n_rows), NULL = natural order */
+  /* optional processing order of rows (length n_rows), NULL = natural order; when it is sorted by
+   * descending degree, the first n_long_rows entries (long rows) are given a whole warp each */
   const int32_t* row_order;
+  int32_t n_long_rows;
   const float* X;     /* [n_cols, d] */
   float* Y;           /* [n_rows, d] or NULL (result only feeds sum/adam) */
   const float* extra; /* optional dense addend [n_rows, d]: y += extra_scale * extra[row] */
@@ -95,6 +97,7 @@ typedef struct srb_encoder_desc {
   const int32_t* colidx;
   const float* vals;
   const int32_t* row_order;
+  int32_t n_long_rows;
   int32_t n;
   int32_t d;
   int32_t n_layers;
@@ -281,6 +284,7 @@ typedef struct srb_graph_csr {
   const int32_t* colidx;
   const float* vals;
   const int32_t* row_order;
+  int32_t n_long_rows;
 } srb_graph_csr;
 
 typedef struct srb_step_desc {
@@ -347,15 +351,23 @@ int64_t srb_sampler_epoch(srb_sampler* s, int32_t batch_size, int32_t batch_cap,
 int64_t srb_sampler_pairs(const srb_sampler* s);
 
 /* ---------------------------------------------------------------------------------------
- * Row-sharded multi-GPU propagation.  rank r owns rows [row_begin, row_end);
- * the epilogue stores every finished row into each peer's copy of the layer output
- * (peer_Y[g], NVLink P2P stores) so the all-gather is fused into the SpMM.
+ * Row-sharded multi-GPU propagation.  Rank r owns the contiguous row block
+ * [row_begin, row_begin + local.n_rows) of the [n_cols, d] tables and the CSR slice A[R_r, :]
+ * (local.rowptr rebased to 0, column ids global).  Every dense operand of `local` (X, Y, extra,
+ * noise, sum_in/out, adam p/m/v) is a full [n_cols, d] buffer indexed by GLOBAL row.  The
+ * epilogue stores each finished row into every rank's copy over NVLink P2P mappings (peer
+ * pointers from torch.distributed._symmetric_memory), so the per-layer all-gather is fused into
+ * the SpMM: peer_Y the layer output, peer_sum the running layer sum, peer_p the Adam-updated
+ * parameters.  NULL arrays disable the respective push.  A cross-rank barrier must separate the
+ * call from the consumers of the pushed rows.
  * ------------------------------------------------------------------------------------- */
 typedef struct srb_spmm_sharded_desc {
-  srb_spmm_desc local; /* rowptr sliced for the owned rows; Y ignored */
-  int32_t row_begin;   /* global index of local row 0 */
+  srb_spmm_desc local;
+  int32_t row_begin;
   int32_t world;
-  float* peer_Y[8];    /* full [n_cols, d] buffers on every rank (own rank included) */
+  float* peer_Y[8];
+  float* peer_sum[8];
+  float* peer_p[8];
 } srb_spmm_sharded_desc;
 
 int srb_spmm_csr_allgather(const srb_spmm_sharded_desc* desc, void* stream);

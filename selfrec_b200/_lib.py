@@ -25,7 +25,7 @@ class SpmmDesc(C.Structure):
     _fields_ = [
         ("rowptr", VP), ("colidx", VP), ("vals", VP),
         ("n_rows", C.c_int32), ("n_cols", C.c_int32), ("d", C.c_int32),
-        ("row_order", VP), ("X", VP), ("Y", VP), ("extra", VP), ("extra_scale", C.c_float),
+        ("row_order", VP), ("n_long_rows", C.c_int32), ("X", VP), ("Y", VP), ("extra", VP), ("extra_scale", C.c_float),
         ("noise_mode", C.c_int32), ("noise", VP), ("eps", C.c_float),
         ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64), ("philox_step_dev", VP),
         ("sum_in", VP), ("sum_out", VP), ("sum_scale", C.c_float),
@@ -36,7 +36,7 @@ class SpmmDesc(C.Structure):
 
 class EncoderDesc(C.Structure):
     _fields_ = [
-        ("rowptr", VP), ("colidx", VP), ("vals", VP), ("row_order", VP),
+        ("rowptr", VP), ("colidx", VP), ("vals", VP), ("row_order", VP), ("n_long_rows", C.c_int32),
         ("n", C.c_int32), ("d", C.c_int32), ("n_layers", C.c_int32), ("include_ego", C.c_int32),
         ("layer_cl", C.c_int32), ("noise_mode", C.c_int32), ("noise", VP), ("eps", C.c_float),
         ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64), ("philox_step_dev", VP),
@@ -78,7 +78,7 @@ class TopkDesc(C.Structure):
 
 
 class GraphCsr(C.Structure):
-    _fields_ = [("rowptr", VP), ("colidx", VP), ("vals", VP), ("row_order", VP)]
+    _fields_ = [("rowptr", VP), ("colidx", VP), ("vals", VP), ("row_order", VP), ("n_long_rows", C.c_int32)]
 
 
 class StepDesc(C.Structure):
@@ -95,7 +95,8 @@ class StepDesc(C.Structure):
 
 
 class SpmmShardedDesc(C.Structure):
-    _fields_ = [("local", SpmmDesc), ("row_begin", C.c_int32), ("world", C.c_int32), ("peer_Y", VP * 8)]
+    _fields_ = [("local", SpmmDesc), ("row_begin", C.c_int32), ("world", C.c_int32), ("peer_Y", VP * 8), ("peer_sum", VP * 8),
+                ("peer_p", VP * 8)]
 
 
 MODEL_IDS = {"MF": 0, "LightGCN": 1, "SimGCL": 2, "XSimGCL": 3, "SGL": 4}

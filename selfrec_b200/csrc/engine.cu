@@ -128,6 +128,7 @@ static int spmm_simple(const srb_step_desc* s, const srb_graph_csr* g, const flo
   p.colidx = g->colidx;
   p.vals = g->vals;
   p.row_order = g->row_order;
+  p.n_long_rows = g->n_long_rows;
   p.n_rows = p.n_cols = s->n_users + s->n_items;
   p.d = s->d;
   p.X = x;
@@ -191,6 +192,7 @@ static int encoder(const srb_step_desc* s, const Ws& w, const srb_graph_csr* g, 
   e.colidx = g->colidx;
   e.vals = g->vals;
   e.row_order = g->row_order;
+  e.n_long_rows = g->n_long_rows;
   e.n = s->n_users + s->n_items;
   e.d = s->d;
   e.n_layers = s->n_layers;

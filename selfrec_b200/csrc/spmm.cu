@@ -16,6 +16,7 @@ struct SpmmArgs {
   const float* vals;
   const int32_t* row_order;
   int32_t n_rows;
+  int32_t n_long;  // leading entries of row_order that get a whole warp
   const float* X;
   float* Y;
   const float* extra;
@@ -35,49 +36,65 @@ struct SpmmArgs {
   const float* ascal;
   float b2, w1, w2, aeps;  // beta2, 1 - beta1, 1 - beta2 (rounded from double like torch's Python floats)
   int32_t world;
-  int32_t row_begin;
-  float* peer[8];
+  int32_t row_begin;  // global index of local row 0 (epilogue tensors are indexed by global row)
+  float* peer[8];      // layer output -> every rank's buffer
+  float* peer_sum[8];  // running sum  -> every rank's buffer
+  float* peer_p[8];    // updated parameters (Adam epilogue) -> every rank's copy
 };
 
 // Mapping: a row vector of D floats lives on LPR = D/8 lanes (two float4 per lane: columns
-// [4*gl, 4*gl+4) and [D/2 + 4*gl, ...)), so a warp works on RPW = 32/LPR rows at once (4 rows for
-// d = 64).  Rows are taken in `row_order` (degree-descending), which keeps the RPW rows of a warp
-// equally long.  Each lane group loads LPR consecutive (col, val) pairs with one coalesced load,
-// then walks them with group-wide shuffles; every X-row gather is two 128-bit ld.global.nc per
-// lane (LPR lanes x 16 B = one contiguous half row), all gathers of a batch are issued before the
-// FMAs so 2*LPR independent loads per lane are in flight.  ~4 warp instructions per non-zero
-// (the first version needed 18 and was issue-bound at 20 % of L2 throughput).
+// [4*gl, 4*gl+4) and [D/2 + 4*gl, ...)).  Rows are taken in `row_order` (degree-descending):
+//   * the first n_long rows (degree >= the host's threshold) get a whole warp each: the 32/LPR lane
+//     groups stride through the row 32 non-zeros at a time and are xor-shuffled together at the end,
+//     so the longest row costs deg/32 dependent iterations instead of deg/LPR;
+//   * the remaining rows are processed RPW = 32/LPR at a time (one per lane group; neighbours in the
+//     sorted order are equally long).
+// Each lane loads one (col, val) pair per iteration (coalesced, prefetched one iteration ahead) and
+// the pairs are walked with group-wide shuffles; every X-row gather is two 128-bit ld.global.nc per
+// lane (LPR lanes x 16 B = one contiguous half row), issued 2*SB at a time before the FMAs.
+// ~4 warp instructions per non-zero (the first version needed 18 and was issue-bound at 20 % of L2
+// throughput).
 template <int D>
 __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmArgs a) {
   constexpr int LPR = D / 8;     // lanes per row
-  constexpr int RPW = 32 / LPR;  // rows per warp
+  constexpr int RPW = 32 / LPR;  // rows per warp (short rows)
   constexpr int HALF = D / 2;
+  constexpr int SB = LPR < 4 ? LPR : 4;  // sub-batch: 2*SB independent 128-bit gathers per lane in flight
   const int lane = threadIdx.x & 31;
   const int grp = lane / LPR;
   const int gl = lane % LPR;
   const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  const int n_quads = (a.n_rows + RPW - 1) / RPW;
+  const int n_long = a.n_long;
+  const int n_items = n_long + (a.n_rows - n_long + RPW - 1) / RPW;
 
-  for (int wq = warp0; wq < n_quads; wq += nwarps) {
-    const int ridx = wq * RPW + grp;
-    const bool valid = ridx < a.n_rows;
+  for (int item = warp0; item < n_items; item += nwarps) {
+    const bool is_long = item < n_long;  // warp-uniform
+    const int ridx = is_long ? item : n_long + (item - n_long) * RPW + grp;
+    bool valid = ridx < a.n_rows;
     int row = 0, p = 0, end = 0;
     if (valid) {
       row = a.row_order ? __ldg(a.row_order + ridx) : ridx;
       p = __ldg(a.rowptr + row);
       end = __ldg(a.rowptr + row + 1);
     }
+    const int stride = is_long ? 32 : LPR;
+    if (is_long) p += grp * LPR;
     float4 acc0 = f4_zero(), acc1 = f4_zero();
+    // (col, val) of the current iteration; padding slots gather row 0 with weight 0 (an L1 hit)
+    int c = 0;
+    float v = 0.f;
+    if (p + gl < end) {
+      c = __ldg(a.colidx + p + gl);
+      v = __ldg(a.vals + p + gl);
+    }
     while (__any_sync(SRB_FULL_MASK, p < end)) {
-      const int idx = p + gl;
-      int c = 0;  // padding slots gather row 0 with weight 0 (an L1 hit) instead of branching
-      float v = 0.f;
-      if (idx < end) {
-        c = __ldg(a.colidx + idx);
-        v = __ldg(a.vals + idx);
+      int cn = 0;
+      float vn = 0.f;
+      if (p + stride + gl < end) {  // prefetch the next iteration's pair
+        cn = __ldg(a.colidx + p + stride + gl);
+        vn = __ldg(a.vals + p + stride + gl);
       }
-      constexpr int SB = LPR < 4 ? LPR : 4;  // sub-batch: 2*SB independent 128-bit gathers per lane in flight
 #pragma unroll
       for (int j0 = 0; j0 < LPR; j0 += SB) {
         if (j0 > 0 && !__any_sync(SRB_FULL_MASK, p + j0 < end)) break;
@@ -97,10 +114,26 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmArgs a) {
           acc1 = f4_fma(vv[j], x1[j], acc1);
         }
       }
-      p += LPR;
+      c = cn;
+      v = vn;
+      p += stride;
+    }
+    if (is_long) {  // combine the lane groups; group 0 owns the row
+#pragma unroll
+      for (int o = LPR; o < 32; o <<= 1) {
+        acc0.x += __shfl_xor_sync(SRB_FULL_MASK, acc0.x, o);
+        acc0.y += __shfl_xor_sync(SRB_FULL_MASK, acc0.y, o);
+        acc0.z += __shfl_xor_sync(SRB_FULL_MASK, acc0.z, o);
+        acc0.w += __shfl_xor_sync(SRB_FULL_MASK, acc0.w, o);
+        acc1.x += __shfl_xor_sync(SRB_FULL_MASK, acc1.x, o);
+        acc1.y += __shfl_xor_sync(SRB_FULL_MASK, acc1.y, o);
+        acc1.z += __shfl_xor_sync(SRB_FULL_MASK, acc1.z, o);
+        acc1.w += __shfl_xor_sync(SRB_FULL_MASK, acc1.w, o);
+      }
+      valid = valid && grp == 0;
     }
     // ---- epilogue (per lane group = per row) ----
-    const size_t off = (size_t)row * D + gl * 4;
+    const size_t off = (size_t)(a.row_begin + row) * D + gl * 4;
     float4 y0 = acc0, y1 = acc1;
     if (a.extra && valid) {
       y0 = f4_fma(a.extra_scale, *reinterpret_cast<const float4*>(a.extra + off), y0);
@@ -115,8 +148,9 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmArgs a) {
         }
       } else {
         const uint32_t stp = a.pstep ? (uint32_t)*a.pstep : 0u;
-        const uint4 r0 = philox4x32_10(make_uint4((uint32_t)row, (uint32_t)gl, a.poff.x, a.poff.y ^ stp), a.pkey);
-        const uint4 r1 = philox4x32_10(make_uint4((uint32_t)row, (uint32_t)(gl + LPR), a.poff.x, a.poff.y ^ stp), a.pkey);
+        const uint32_t grow = (uint32_t)(a.row_begin + row);
+        const uint4 r0 = philox4x32_10(make_uint4(grow, (uint32_t)gl, a.poff.x, a.poff.y ^ stp), a.pkey);
+        const uint4 r1 = philox4x32_10(make_uint4(grow, (uint32_t)(gl + LPR), a.poff.x, a.poff.y ^ stp), a.pkey);
         n0 = make_float4(u32_to_unit(r0.x), u32_to_unit(r0.y), u32_to_unit(r0.z), u32_to_unit(r0.w));
         n1 = make_float4(u32_to_unit(r1.x), u32_to_unit(r1.y), u32_to_unit(r1.z), u32_to_unit(r1.w));
       }
@@ -134,12 +168,11 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmArgs a) {
       st4(a.Y + off, y0);
       st4(a.Y + off + HALF, y1);
     }
-    if (a.world > 0) {
-      const size_t goff = (size_t)(a.row_begin + row) * D + gl * 4;
+    if (a.world > 0 && a.peer[0]) {  // fused all-gather: NVLink P2P stores into every rank's layer buffer
 #pragma unroll 1
       for (int g = 0; g < a.world; ++g) {
-        st4(a.peer[g] + goff, y0);
-        st4(a.peer[g] + goff + HALF, y1);
+        st4(a.peer[g] + off, y0);
+        st4(a.peer[g] + off + HALF, y1);
       }
     }
     if (a.sum_out) {
@@ -148,8 +181,17 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmArgs a) {
         s0 = f4_add(s0, *reinterpret_cast<const float4*>(a.sum_in + off));
         s1 = f4_add(s1, *reinterpret_cast<const float4*>(a.sum_in + off + HALF));
       }
-      st4(a.sum_out + off, f4_scale(a.sum_scale, s0));
-      st4(a.sum_out + off + HALF, f4_scale(a.sum_scale, s1));
+      s0 = f4_scale(a.sum_scale, s0);
+      s1 = f4_scale(a.sum_scale, s1);
+      st4(a.sum_out + off, s0);
+      st4(a.sum_out + off + HALF, s1);
+      if (a.world > 0 && a.peer_sum[0]) {
+#pragma unroll 1
+        for (int g = 0; g < a.world; ++g) {
+          st4(a.peer_sum[g] + off, s0);
+          st4(a.peer_sum[g] + off + HALF, s1);
+        }
+      }
     }
     if (a.ap) {
       const float step_size = a.ascal[0];
@@ -171,6 +213,10 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmArgs a) {
         st4(a.ap + o2, p4);
         st4(a.am + o2, m);
         st4(a.av + o2, v4);
+        if (a.world > 0 && a.peer_p[0]) {
+#pragma unroll 1
+          for (int g = 0; g < a.world; ++g) st4(a.peer_p[g] + o2, p4);
+        }
       }
     }
   }
@@ -179,8 +225,9 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmArgs a) {
 static int launch_spmm(const SpmmArgs& a, int d, cudaStream_t st) {
   if (a.n_rows == 0) return SRB_OK;
   const int threads = 256;
-  const int rows_per_block = (threads / 32) * (32 / (d / 8));
-  long long blocks = ((long long)a.n_rows + rows_per_block - 1) / rows_per_block;
+  const int rpw = 32 / (d / 8);
+  const long long items = (long long)a.n_long + ((long long)a.n_rows - a.n_long + rpw - 1) / rpw;
+  long long blocks = (items + threads / 32 - 1) / (threads / 32);
   const long long cap = (long long)sm_count() * 8;  // 8 x 256 threads = full residency
   if (blocks > cap) blocks = cap;
   switch (d) {
@@ -205,6 +252,7 @@ static int fill_args(const srb_spmm_desc* d, SpmmArgs& a) {
   a.vals = d->vals;
   a.row_order = d->row_order;
   a.n_rows = d->n_rows;
+  a.n_long = (d->row_order && d->n_long_rows > 0) ? (d->n_long_rows < d->n_rows ? d->n_long_rows : d->n_rows) : 0;
   a.X = d->X;
   a.Y = d->Y;
   a.extra = d->extra;
@@ -228,7 +276,7 @@ static int fill_args(const srb_spmm_desc* d, SpmmArgs& a) {
   a.aeps = d->adam_eps;
   a.world = 0;
   a.row_begin = 0;
-  for (int g = 0; g < 8; ++g) a.peer[g] = nullptr;
+  for (int g = 0; g < 8; ++g) a.peer[g] = a.peer_sum[g] = a.peer_p[g] = nullptr;
   return SRB_OK;
 }
 
@@ -243,15 +291,24 @@ extern "C" int srb_spmm_csr(const srb_spmm_desc* desc, void* stream) {
 extern "C" int srb_spmm_csr_allgather(const srb_spmm_sharded_desc* desc, void* stream) {
   SRB_REQUIRE(desc != nullptr, "spmm_allgather: null desc");
   SRB_REQUIRE(desc->world >= 1 && desc->world <= 8, "spmm_allgather: world must be 1..8");
+  SRB_REQUIRE(desc->row_begin >= 0 && desc->row_begin + desc->local.n_rows <= desc->local.n_cols,
+              "spmm_allgather: owned rows [%d, %d) outside [0, %d)", desc->row_begin, desc->row_begin + desc->local.n_rows,
+              desc->local.n_cols);
   srb::SpmmArgs a;
   SRB_TRY(srb::fill_args(&desc->local, a));
-  a.Y = nullptr;
   a.world = desc->world;
   a.row_begin = desc->row_begin;
+  const bool has_y = desc->peer_Y[0] != nullptr, has_s = desc->peer_sum[0] != nullptr, has_p = desc->peer_p[0] != nullptr;
+  SRB_REQUIRE(!has_s || desc->local.sum_out, "spmm_allgather: peer_sum needs the sum epilogue");
+  SRB_REQUIRE(!has_p || desc->local.adam_p, "spmm_allgather: peer_p needs the Adam epilogue");
   for (int g = 0; g < desc->world; ++g) {
-    SRB_REQUIRE(desc->peer_Y[g] != nullptr, "spmm_allgather: null peer buffer %d", g);
-    SRB_REQUIRE(desc->peer_Y[g] != desc->local.X, "spmm_allgather: peer buffer aliases X");
+    SRB_REQUIRE((desc->peer_Y[g] != nullptr) == has_y && (desc->peer_sum[g] != nullptr) == has_s &&
+                    (desc->peer_p[g] != nullptr) == has_p,
+                "spmm_allgather: peer buffer %d inconsistent", g);
+    SRB_REQUIRE(!has_y || desc->peer_Y[g] != desc->local.X, "spmm_allgather: peer buffer aliases X");
     a.peer[g] = desc->peer_Y[g];
+    a.peer_sum[g] = desc->peer_sum[g];
+    a.peer_p[g] = desc->peer_p[g];
   }
   return srb::launch_spmm(a, desc->local.d, (cudaStream_t)stream);
 }
@@ -283,6 +340,7 @@ extern "C" int srb_encoder_forward(const srb_encoder_desc* e, void* stream) {
     s.colidx = e->colidx;
     s.vals = e->vals;
     s.row_order = e->row_order;
+    s.n_long_rows = e->n_long_rows;
     s.n_rows = e->n;
     s.n_cols = e->n;
     s.d = e->d;

@@ -13,6 +13,7 @@ from . import _lib
 from ._lib import SrbError
 
 _SUPPORTED_D = (32, 64, 128)
+LONG_ROW_NNZ = 128  # rows at least this long are processed by a whole warp (srb_spmm_desc.n_long_rows)
 
 
 def _stream():
@@ -63,6 +64,7 @@ class SparseAdj:
         self.shape = tuple(csr.shape)
         self.device = torch.device("cpu")
         self.rowptr = self.colidx = self.vals = self.row_order = None
+        self.n_long = 0
         self._t = None  # transposed handle (backward), built lazily
         self._symmetric = None
 
@@ -79,6 +81,7 @@ class SparseAdj:
         # long rows first: evens out the tail of the warp-per-row kernel on power-law graphs
         deg = np.diff(csr.indptr)
         self.row_order = torch.from_numpy(np.argsort(-deg, kind="stable").astype(np.int32)).to(dev)
+        self.n_long = int((deg >= LONG_ROW_NNZ).sum())  # rows that get a whole warp in the SpMM
         self.device = dev
         return self
 
@@ -126,6 +129,7 @@ class SparseAdj:
     def graph_struct(self):
         g = _lib.GraphCsr()
         g.rowptr, g.colidx, g.vals, g.row_order = _p(self.rowptr), _p(self.colidx), _p(self.vals), _p(self.row_order)
+        g.n_long_rows = self.n_long
         return g
 
 
@@ -142,6 +146,7 @@ def _spmm_raw(adj, x, y=None, **epi):
     desc = _lib.SpmmDesc()
     desc.rowptr, desc.colidx, desc.vals = _p(adj.rowptr), _p(adj.colidx), _p(adj.vals)
     desc.row_order = _p(adj.row_order)
+    desc.n_long_rows = adj.n_long
     desc.n_rows, desc.n_cols, desc.d = n_rows, n_cols, d
     desc.X = _p(x)
     desc.Y = _p(y)
@@ -199,6 +204,7 @@ def encoder_forward(adj, e0, n_layers, include_ego, noise=None, eps=0.0, layer_c
     w1 = torch.empty_like(e0)
     desc = _lib.EncoderDesc()
     desc.rowptr, desc.colidx, desc.vals, desc.row_order = _p(adj.rowptr), _p(adj.colidx), _p(adj.vals), _p(adj.row_order)
+    desc.n_long_rows = adj.n_long
     desc.n, desc.d, desc.n_layers, desc.include_ego, desc.layer_cl = n, d, n_layers, int(include_ego), int(layer_cl)
     if noise is not None:
         noise = _f32c(noise, "encoder noise")
@@ -358,6 +364,8 @@ def score_topk(user_emb, item_emb, users, rated_ptr, rated_idx, k, impl=0):
     if rated_ptr is not None:
         rated_ptr, rated_idx = _i32(rated_ptr, dev), _i32(rated_idx, dev)
         desc.rated_ptr, desc.rated_idx = _p(rated_ptr), _p(rated_idx)
+    if impl == 0:  # auto: tensor-core path for the embedding size it is written for, else the CUDA-core kernel
+        impl = 2 if (d == 64 and item_emb.shape[0] >= 1024) else 1
     desc.k, desc.out_ids, desc.out_scores, desc.impl = k, _p(out_ids), _p(out_sc), impl
     ws = None
     if impl == 2:

@@ -72,9 +72,9 @@ def test_xsimgcl_step_full_size_vs_oracle(yelp, orc, in_tmp_cwd):
     got = eng.params.cpu().numpy()
     # Step 1 of Adam moves a weight by lr * g / (|g| + eps).  Where |g| >> eps = 1e-8 this is +-lr and the
     # parameters must agree to the embedding tolerance; where |g| ~ eps the quotient amplifies the fp32
-    # rounding of g (relative 2e-4 after three propagation hops) by 1/(|g| + eps): bound that explicitly.
+    # rounding of g by 1/(|g| + eps): bound that explicitly.
     g = np.abs(out["grad"])
-    dg = 2e-4 * g + 2e-11
+    dg = 2e-6 * g + 5e-10  # measured: GPU vs oracle gradient differs by <= 3.5e-10 absolute (tools/grad_diag.py)
     tol = 1e-4 * np.abs(P) + 1e-7 + 1e-3 * dg / (g + 1e-8)
     bad = np.abs(got - P) > tol
     assert not bad.any(), (int(bad.sum()), float(np.abs(got - P)[bad].max()), float(g[bad].min()), float(g[bad].max()))
