@@ -259,6 +259,8 @@ typedef struct srb_topk_desc {
 } srb_topk_desc;
 
 int64_t srb_topk_workspace_bytes(int32_t n_q, int32_t n_items, int32_t d, int32_t k);
+/* byte offset (inside the impl-2 workspace) of the int32 count of users the exact fallback re-ran */
+int64_t srb_topk_fallback_count_offset(int32_t n_q, int32_t n_items);
 int srb_score_topk(const srb_topk_desc* desc, void* stream);
 /* Mask-free top-k of precomputed score rows [n_q, n_items] (models whose predict() is not one
  * dot product, e.g. BUIR.py); same selection rule.  The caller applies the -10e8 mask. */

@@ -13,7 +13,9 @@
 //           dV1 += G V2 (registers, one atomic pass), dV2 += G^T V1 (red.v4 per tile)
 //                                                                            (6 n^2 d flop)
 //   finish  back through F.normalize, loss = mean(lse - S_ii)
+#include <stdlib.h>
 #include "common.cuh"
+#include "infonce_tc.cuh"
 
 namespace srb {
 
@@ -403,11 +405,101 @@ __global__ void __launch_bounds__(256) nce_finish_kernel(const NceArgs a) {
 }
 
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
-static inline int nce_np(int n) { return (int)align_up(n > 0 ? n : 1, NCE_T); }
+static inline int nce_np(int n) { return (int)align_up(n > 0 ? n : 1, 128); }  // 128: tile edge of the tensor-core path
 
 static int64_t nce_problem_floats(int np, int d) {
-  // V1 V2 V1T V2T dV1 dV2: 6 * np * d ; inv1 inv2 diag: 3 * np ; part_m part_l: 2 * splits * np ; loss_acc (padded)
-  return 6ll * np * d + 3ll * np + 2ll * NCE_MAX_SPLITS * np + 64;
+  // V1 V2 V1T V2T dV1 dV2 + TF32-rounded V1 V2 V1T V2T: 10 * np * d ; inv1 inv2 diag: 3 * np ;
+  // part_m part_l: 2 * splits * np ; loss_acc (padded)
+  return 10ll * np * d + 3ll * np + 2ll * NCE_MAX_SPLITS * np + 64;
+}
+
+// 0 = auto (tensor cores when d == 64), 1 = CUDA-core tiles, 2 = tensor cores
+static int nce_impl() {
+  static int impl = -1;
+  if (impl < 0) {
+    const char* e = getenv("SRB_NCE_IMPL");
+    impl = e ? atoi(e) : 0;
+  }
+  return impl;
+}
+
+__global__ void __launch_bounds__(256) nce_round_kernel(const float* __restrict__ src, float* __restrict__ dst, long long n4) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    reinterpret_cast<float4*>(dst)[i] = make_float4(to_tf32_rna(v.x), to_tf32_rna(v.y), to_tf32_rna(v.z), to_tf32_rna(v.w));
+  }
+}
+
+// tensor-core pipeline: prep (exact) -> round copies -> LSE -> GRAD-A / GRAD-B -> finish
+static int nce_launch_tc(const NceArgs& a, int n_problems, cudaStream_t st) {
+  const int np = a.np;
+  const int d = NT_D;
+  {
+    dim3 grid((np + 7) / 8, n_problems);
+    nce_prep_kernel<64><<<grid, 256, 0, st>>>(a);
+    SRB_TRY(post_launch("nce_prep_kernel"));
+  }
+  NtMaps maps;
+  NtArgs t;
+  t.np = np;
+  t.inv_tau = a.inv_tau;
+  const int row_blocks = np / NT_T;
+  int splits = (2 * sm_count() + row_blocks * n_problems - 1) / (row_blocks * n_problems);
+  if (splits < 1) splits = 1;
+  if (splits > NT_MAX_SPLITS) splits = NT_MAX_SPLITS;
+  if (splits > row_blocks) splits = row_blocks;
+  t.splits = splits;
+  const long long nd = (long long)np * d;
+  for (int q = 0; q < n_problems; ++q) {
+    const NceProblem& p = a.p[q];
+    // rounded copies live behind dV2: V1R V2R V1TR V2TR
+    float* r = p.dV2 + nd;
+    nce_round_kernel<<<64, 256, 0, st>>>(p.V1, r, 4 * nd / 4);  // V1 V2 V1T V2T are contiguous
+    SRB_TRY(post_launch("nce_round_kernel"));
+    SRB_REQUIRE(make_tmap_f32_rows(&maps.v1[q], r, (uint64_t)np, d, NT_T) == 0 &&
+                    make_tmap_f32_rows(&maps.v2[q], r + nd, (uint64_t)np, d, NT_T) == 0 &&
+                    make_tmap_f32_rows(&maps.v1t[q], r + 2 * nd, (uint64_t)d, (uint64_t)np, NT_D) == 0 &&
+                    make_tmap_f32_rows(&maps.v2t[q], r + 3 * nd, (uint64_t)d, (uint64_t)np, NT_D) == 0,
+                "infonce: cuTensorMapEncodeTiled failed");
+    NtProblem& o = t.p[q];
+    o.n = p.n;
+    o.n_dev = p.n_dev;
+    o.weight = p.weight;
+    o.diag = p.diag;
+    o.part_m = p.part_m;
+    o.part_l = p.part_l;
+    o.dV1 = p.dV1;
+    o.dV2 = p.dV2;
+    o.loss_acc = p.loss_acc;
+  }
+  for (int q = n_problems; q < 4; ++q) {
+    maps.v1[q] = maps.v1[0];
+    maps.v2[q] = maps.v2[0];
+    maps.v1t[q] = maps.v1t[0];
+    maps.v2t[q] = maps.v2t[0];
+    t.p[q] = t.p[0];
+  }
+  const size_t smem = NtSmem::total + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SRB_TRY(check_cuda(cudaFuncSetAttribute(nce_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "nce tc attr"));
+    SRB_TRY(check_cuda(cudaFuncSetAttribute(nce_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "nce tc attr"));
+    SRB_TRY(check_cuda(cudaFuncSetAttribute(nce_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "nce tc attr"));
+    attr_done = true;
+  }
+  dim3 grid(row_blocks, splits, n_problems);
+  nce_tc_kernel<0><<<grid, NT_THREADS, smem, st>>>(maps, t);
+  SRB_TRY(post_launch("nce_tc_kernel<lse>"));
+  nce_tc_kernel<1><<<grid, NT_THREADS, smem, st>>>(maps, t);
+  SRB_TRY(post_launch("nce_tc_kernel<grad_a>"));
+  nce_tc_kernel<2><<<grid, NT_THREADS, smem, st>>>(maps, t);
+  SRB_TRY(post_launch("nce_tc_kernel<grad_b>"));
+  {
+    dim3 g2((np + 7) / 8, n_problems);
+    nce_finish_kernel<64><<<g2, 256, 0, st>>>(a);
+    SRB_TRY(post_launch("nce_finish_kernel"));
+  }
+  return SRB_OK;
 }
 
 template <int D>
@@ -504,7 +596,7 @@ extern "C" int srb_infonce_fwd_bwd(const srb_infonce_desc* d, void* stream) {
     p.V2T = base + 3 * nd;
     p.dV1 = base + 4 * nd;
     p.dV2 = base + 5 * nd;
-    float* t = base + 6 * nd;
+    float* t = base + 10 * nd;  // [6 nd, 10 nd): TF32-rounded copies (tensor-core path)
     p.inv1 = t;
     p.inv2 = t + a.np;
     p.diag = t + 2 * a.np;
@@ -513,6 +605,9 @@ extern "C" int srb_infonce_fwd_bwd(const srb_infonce_desc* d, void* stream) {
     p.loss_acc = t + 3 * a.np + 2ll * srb::NCE_MAX_SPLITS * a.np;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  const int impl = srb::nce_impl();
+  if (d->d == 64 && d->b_cos && impl != 1) return srb::nce_launch_tc(a, d->n_problems, st);
+  SRB_REQUIRE(impl != 2, "infonce: SRB_NCE_IMPL=2 (tensor cores) needs d == 64 and b_cos");
   switch (d->d) {
     case 32: return srb::nce_launch<32>(a, d->n_problems, st);
     case 64: return srb::nce_launch<64>(a, d->n_problems, st);

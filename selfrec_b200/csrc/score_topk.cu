@@ -33,6 +33,7 @@ struct TopkArgs {
   float* out_scores;
   const int32_t* q_map;    // optional: output row of query q (fallback path of impl 2)
   const int32_t* n_q_dev;  // optional: device-side query count (<= n_q)
+  int32_t q_skip;          // first q_skip queries are handled elsewhere (fast fallback)
 };
 
 template <int D>
@@ -42,7 +43,7 @@ __global__ void __launch_bounds__(256) score_topk_kernel(const TopkArgs a) {
   float (*Is)[D + 1] = reinterpret_cast<float (*)[D + 1]>(tk_smem + D * TK_TM);       // [128][D+1]
   const int lane = threadIdx.x & 31;
   const int ty = threadIdx.x >> 5;  // warp id: users ty*4 .. ty*4+3 of the CTA tile
-  const int q0 = blockIdx.x * TK_TM;
+  const int q0 = a.q_skip + blockIdx.x * TK_TM;
   const int n_q = a.n_q_dev ? min(*a.n_q_dev, a.n_q) : a.n_q;
   if (q0 >= n_q) return;
 
@@ -234,14 +235,96 @@ static int launch_topk(const TopkArgs& a, cudaStream_t st) {
     SRB_TRY(check_cuda(cudaFuncSetAttribute(score_topk_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "topk smem attr"));
     attr_done = true;
   }
-  const int blocks = (a.n_q + TK_TM - 1) / TK_TM;
+  const int blocks = (a.n_q - a.q_skip + TK_TM - 1) / TK_TM;
+  if (blocks <= 0) return SRB_OK;
   score_topk_kernel<D><<<blocks, 256, smem, st>>>(a);
   return post_launch("score_topk_kernel");
 }
 
-// exact re-run of the users impl 2 could not certify (device-side list and count)
+// ---- fallback of impl 2: exact re-run of the users it could not certify (device-side list) ----
+// Fast path for the first `cap` of them: exact score rows spread over many CTAs + one warp per user
+// for the sequential top-k (a handful of users must not cost a full impl-1 block pass, ~1.6 ms).
+template <int D>
+__global__ void __launch_bounds__(256) fb_score_kernel(const float* __restrict__ user_emb, const float* __restrict__ item_emb,
+                                                      const int32_t* __restrict__ fb_users, const int32_t* __restrict__ fb_count,
+                                                      const int32_t* __restrict__ rated_ptr, const int32_t* __restrict__ rated_idx,
+                                                      int n_items, float* __restrict__ scratch) {
+  const int slot = blockIdx.y;
+  if (slot >= *fb_count) return;
+  __shared__ float us[D];
+  const int u = fb_users[slot];
+  for (int k = threadIdx.x; k < D; k += blockDim.x) us[k] = user_emb[(size_t)u * D + k];
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_items) return;
+  const float* it = item_emb + (size_t)i * D;
+  float acc = 0.f;
+#pragma unroll 8
+  for (int k4 = 0; k4 < D / 4; ++k4) {
+    const float4 v = ldg4(it + k4 * 4);
+    acc = fmaf(us[k4 * 4 + 0], v.x, acc);
+    acc = fmaf(us[k4 * 4 + 1], v.y, acc);
+    acc = fmaf(us[k4 * 4 + 2], v.z, acc);
+    acc = fmaf(us[k4 * 4 + 3], v.w, acc);
+  }
+  if (rated_ptr) {  // binary search of item i in the user's sorted rated list
+    int lo = rated_ptr[u], hi = rated_ptr[u + 1];
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      const int v = rated_idx[mid];
+      if (v < i) lo = mid + 1; else hi = mid;
+    }
+    if (lo < rated_ptr[u + 1] && rated_idx[lo] == i) acc = TK_MASKED;
+  }
+  scratch[(size_t)slot * n_items + i] = acc;
+}
+
+__global__ void __launch_bounds__(256) fb_topk_kernel(const float* scratch, const int32_t* fb_rows, const int32_t* fb_count, int cap,
+                                                      int n_items, int k, int32_t* out_ids, float* out_scores) {
+  const int lane = threadIdx.x & 31;
+  const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (slot >= cap || slot >= *fb_count) return;
+  float ls = -INFINITY;
+  int li = -1;
+  const float* row = scratch + (size_t)slot * n_items;
+  for (int n0 = 0; n0 < n_items; n0 += 32) {
+    const int id = n0 + lane;
+    const float sc = (id < n_items) ? row[id] : -INFINITY;
+    float thr = __shfl_sync(SRB_FULL_MASK, ls, k - 1);
+    unsigned m = __ballot_sync(SRB_FULL_MASK, sc > thr);
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      const float cs = __shfl_sync(SRB_FULL_MASK, sc, src);
+      const int cid = __shfl_sync(SRB_FULL_MASK, id, src);
+      thr = __shfl_sync(SRB_FULL_MASK, ls, k - 1);
+      if (cs > thr) {
+        const int pos = __popc(__ballot_sync(SRB_FULL_MASK, lane < k && ls > cs));
+        const float ps = __shfl_up_sync(SRB_FULL_MASK, ls, 1);
+        const int pi = __shfl_up_sync(SRB_FULL_MASK, li, 1);
+        if (lane > pos && lane < k) ls = ps, li = pi;
+        if (lane == pos) ls = cs, li = cid;
+      }
+    }
+  }
+  if (lane < k) {
+    const size_t orow = (size_t)fb_rows[slot];
+    out_ids[orow * k + lane] = li;
+    out_scores[orow * k + lane] = ls;
+  }
+}
+
 int score_topk_fallback(const srb_topk_desc* d, const int32_t* fb_users, const int32_t* fb_rows, const int32_t* fb_count,
-                        cudaStream_t st) {
+                        float* scratch, int fb_cap, cudaStream_t st) {
+  // fast path: up to fb_cap users
+  dim3 grid((d->n_items + 255) / 256, fb_cap);
+  fb_score_kernel<64><<<grid, 256, 0, st>>>(d->user_emb, d->item_emb, fb_users, fb_count, d->rated_ptr, d->rated_idx, d->n_items,
+                                            scratch);
+  SRB_TRY(post_launch("fb_score_kernel"));
+  fb_topk_kernel<<<(fb_cap + 7) / 8, 256, 0, st>>>(scratch, fb_rows, fb_count, fb_cap, d->n_items, d->k, d->out_ids, d->out_scores);
+  SRB_TRY(post_launch("fb_topk_kernel"));
+  // slow path: everyone beyond fb_cap goes through the impl-1 kernel (CTAs without work exit at once)
+  if (d->n_q <= fb_cap) return SRB_OK;
   TopkArgs a;
   a.user_emb = d->user_emb;
   a.item_emb = d->item_emb;
@@ -255,6 +338,7 @@ int score_topk_fallback(const srb_topk_desc* d, const int32_t* fb_users, const i
   a.out_scores = d->out_scores;
   a.q_map = fb_rows;
   a.n_q_dev = fb_count;
+  a.q_skip = fb_cap;
   return launch_topk<64>(a, st);
 }
 
@@ -285,6 +369,7 @@ extern "C" int srb_score_topk(const srb_topk_desc* d, void* stream) {
   a.out_scores = d->out_scores;
   a.q_map = nullptr;
   a.n_q_dev = nullptr;
+  a.q_skip = 0;
   switch (d->d) {
     case 32: return srb::launch_topk<32>(a, (cudaStream_t)stream);
     case 64: return srb::launch_topk<64>(a, (cudaStream_t)stream);

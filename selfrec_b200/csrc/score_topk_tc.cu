@@ -12,8 +12,9 @@
 //            warp 1   MMA issuer : tcgen05.mma kind::tf32, M=128 (users) x N=128 (items) x K=8,
 //                                  2 user halves x 8 k-steps per tile, accumulators in TMEM
 //                                  (2 stages x 2 halves x 128 columns = all 512 columns)
-//            warps 2-9 epilogue  : tcgen05.ld (lane = user row), rated-item cursor, per-thread
-//                                  top-32 candidate list (replace-min) in shared memory
+//            warps 2-9 epilogue  : tcgen05.ld (lane = user row, next group's load in flight while one
+//                                  is processed), rated-item cursor, per-thread top-32 candidate
+//                                  min-heap in shared memory
 //          The raw fp32 tables are fed to the tensor core, which reads them as TF32 (low 13
 //          mantissa bits ignored): scores carry <= 2^-9 ||u|| ||i|| error -- candidates only.
 // Stage 3  tc_rescore_kernel    warp per user: exact fp32 fma-chain scores of the 32 candidates
@@ -179,7 +180,7 @@ tc_score_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_const
     float* cs = reinterpret_cast<float*>(sm + TcSmem::cand_s_off);
     int32_t* ci = reinterpret_cast<int32_t*>(sm + TcSmem::cand_i_off);
     float thr = -INFINITY;
-    int cnt = 0, min_pos = 0;
+    int cnt = 0;
     int cur = 0, cend = 0, next_rated = 0x7fffffff;
     if (active && a.rated_ptr) {
       const int u = a.users[q];
@@ -187,57 +188,86 @@ tc_score_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_const
       cend = a.rated_ptr[u + 1];
       if (cur < cend) next_rated = a.rated_idx[cur];
     }
+    // candidate list = min-heap of 32 (score, id) in shared memory, column `tix`; thr = heap root
+    auto process_group = [&](const uint32_t (&r)[32], int g0) {
+      uint32_t mask = 0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(r[j]) > thr) ? (1u << j) : 0u;
+      if (g0 + 32 > a.n_items) mask &= (g0 < a.n_items) ? (0xffffffffu >> (g0 + 32 - a.n_items)) : 0u;  // zero-filled OOB rows
+      if (!active) mask = 0;
+      // rated items never become candidates: walk the sorted rated list through this group
+      while (next_rated < g0 + 32) {
+        if (next_rated >= g0) mask &= ~(1u << (next_rated - g0));
+        ++cur;
+        next_rated = (cur < cend) ? a.rated_idx[cur] : 0x7fffffff;
+      }
+      while (mask) {
+        const int j = __ffs(mask) - 1;
+        mask &= mask - 1;
+        float sc = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj)
+          if (jj == j) sc = __uint_as_float(r[jj]);
+        if (!(sc > thr)) continue;  // thr may have risen inside this group
+        const int id = g0 + j;
+        if (cnt < TC_CAND) {
+          // filling: sift up
+          int pos = cnt++;
+          while (pos > 0) {
+            const int par = (pos - 1) >> 1;
+            const float pv = cs[par * 256 + tix];
+            if (!(sc < pv)) break;
+            cs[pos * 256 + tix] = pv;
+            ci[pos * 256 + tix] = ci[par * 256 + tix];
+            pos = par;
+          }
+          cs[pos * 256 + tix] = sc;
+          ci[pos * 256 + tix] = id;
+          if (cnt == TC_CAND) thr = cs[tix];
+        } else {
+          // replace the root (current minimum) and sift down
+          int pos = 0;
+#pragma unroll 1
+          for (;;) {
+            const int l = 2 * pos + 1;
+            if (l >= TC_CAND) break;
+            int c = l;
+            float cv = cs[l * 256 + tix];
+            if (l + 1 < TC_CAND) {
+              const float rv = cs[(l + 1) * 256 + tix];
+              if (rv < cv) cv = rv, c = l + 1;
+            }
+            if (!(cv < sc)) break;
+            cs[pos * 256 + tix] = cv;
+            ci[pos * 256 + tix] = ci[c * 256 + tix];
+            pos = c;
+          }
+          cs[pos * 256 + tix] = sc;
+          ci[pos * 256 + tix] = id;
+          thr = cs[tix];
+        }
+      }
+    };
     for (int t = 0; t < n_tiles; ++t) {
       const int acc = t & 1;
       mbar_wait(bar_tfull + acc, (t >> 1) & 1);
       fence_after_sync();
       const int n0 = t * TC_TN;
-#pragma unroll 1
-      for (int g = 0; g < TC_TN / 32; ++g) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem + ((uint32_t)(quarter * 32) << 16) + acc * 256 + half * 128 + g * 32, r);
-        tmem_ld_wait();
-        const int g0 = n0 + g * 32;
-        uint32_t mask = 0;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(r[j]) > thr) ? (1u << j) : 0u;
-        if (g0 + 32 > a.n_items) mask &= (g0 < a.n_items) ? (0xffffffffu >> (g0 + 32 - a.n_items)) : 0u;  // zero-filled OOB rows
-        if (!active) mask = 0;
-        // rated items never become candidates: walk the sorted rated list through this group
-        while (next_rated < g0 + 32) {
-          if (next_rated >= g0) mask &= ~(1u << (next_rated - g0));
-          ++cur;
-          next_rated = (cur < cend) ? a.rated_idx[cur] : 0x7fffffff;
-        }
-        while (mask) {
-          const int j = __ffs(mask) - 1;
-          mask &= mask - 1;
-          float sc = 0.f;
-#pragma unroll
-          for (int jj = 0; jj < 32; ++jj)
-            if (jj == j) sc = __uint_as_float(r[jj]);
-          if (!(sc > thr)) continue;  // thr may have risen inside this group
-          int pos;
-          if (cnt < TC_CAND) {
-            pos = cnt++;
-          } else {
-            pos = min_pos;
-          }
-          cs[pos * 256 + tix] = sc;
-          ci[pos * 256 + tix] = g0 + j;
-          if (cnt == TC_CAND) {  // list full: threshold = current minimum
-            float mn = INFINITY;
-            int mp = 0;
-#pragma unroll 8
-            for (int p = 0; p < TC_CAND; ++p) {
-              const float v = cs[p * 256 + tix];
-              if (v < mn) mn = v, mp = p;
-            }
-            thr = mn;
-            min_pos = mp;
-          }
-        }
-      }
+      const uint32_t tbase = tmem + ((uint32_t)(quarter * 32) << 16) + acc * 256 + half * 128;
+      // two register buffers: the load of group g+1 is in flight while group g is processed
+      uint32_t r0[32], r1[32];
+      tmem_ld_32x32(tbase, r0);
+      tmem_ld_wait();
+      tmem_ld_32x32(tbase + 32, r1);
+      process_group(r0, n0);
+      tmem_ld_wait();
+      tmem_ld_32x32(tbase + 64, r0);
+      process_group(r1, n0 + 32);
+      tmem_ld_wait();
+      tmem_ld_32x32(tbase + 96, r1);
+      process_group(r0, n0 + 64);
+      tmem_ld_wait();
+      process_group(r1, n0 + 96);
       fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + acc);
@@ -361,10 +391,19 @@ struct TcWorkspace {
   int32_t* fb_count;
   int32_t* fb_rows;
   int32_t* fb_users;
+  float* fb_scratch;  // [fb_cap][n_items] exact score rows of the users re-run by the fast fallback
+  int32_t fb_cap;
   int64_t bytes;
 };
 
-static TcWorkspace tc_carve(char* base, int n_q) {
+static int tc_fb_cap(int n_items) {
+  long long cap = (64ll << 20) / ((long long)n_items * 4);  // at most 64 MB of scratch
+  if (cap > 256) cap = 256;
+  if (cap < 8) cap = 8;
+  return (int)cap;
+}
+
+static TcWorkspace tc_carve(char* base, int n_q, int n_items) {
   TcWorkspace w;
   const int64_t n_q_pad = ((int64_t)n_q + 255) / 256 * 256 + 256;
   int64_t off = 0;
@@ -383,22 +422,24 @@ static TcWorkspace tc_carve(char* base, int n_q) {
   w.fb_count = (int32_t*)take(16);
   w.fb_rows = (int32_t*)take((int64_t)n_q * 4);
   w.fb_users = (int32_t*)take((int64_t)n_q * 4);
+  w.fb_cap = tc_fb_cap(n_items);
+  w.fb_scratch = (float*)take((int64_t)w.fb_cap * n_items * 4);
   w.bytes = off;
   return w;
 }
 
 int score_topk_fallback(const srb_topk_desc* d, const int32_t* fb_users, const int32_t* fb_rows, const int32_t* fb_count,
-                        cudaStream_t st);  // score_topk.cu
+                        float* scratch, int fb_cap, cudaStream_t st);  // score_topk.cu
 
 int score_topk_tc(const srb_topk_desc* d, cudaStream_t st) {
   SRB_REQUIRE(d->d == TC_D, "topk impl 2 (tcgen05) supports d=64 only (got %d)", d->d);
   const int n_q = d->n_q;
-  const TcWorkspace need = tc_carve(nullptr, n_q);
+  const TcWorkspace need = tc_carve(nullptr, n_q, d->n_items);
   SRB_REQUIRE(d->workspace && d->workspace_bytes >= need.bytes, "topk impl 2: workspace too small (%lld < %lld)",
               (long long)d->workspace_bytes, (long long)need.bytes);
   SRB_REQUIRE(((uintptr_t)d->workspace & 255) == 0, "topk impl 2: workspace must be 256-byte aligned");
   SRB_REQUIRE(((uintptr_t)d->item_emb & 15) == 0, "topk impl 2: item_emb must be 16-byte aligned");
-  TcWorkspace w = tc_carve((char*)d->workspace, n_q);
+  TcWorkspace w = tc_carve((char*)d->workspace, n_q, d->n_items);
   const int n_q_pad = (n_q + 255) / 256 * 256 + 256;
   SRB_TRY(check_cuda(cudaMemsetAsync(w.bmax, 0, 16, st), "tc memset"));
   SRB_TRY(check_cuda(cudaMemsetAsync(w.fb_count, 0, 16, st), "tc memset"));
@@ -459,15 +500,22 @@ int score_topk_tc(const srb_topk_desc* d, cudaStream_t st) {
   r.fb_users = w.fb_users;
   tc_rescore_kernel<<<(n_q + 7) / 8, 256, 0, st>>>(r);
   SRB_TRY(post_launch("tc_rescore_kernel"));
-  return score_topk_fallback(d, w.fb_users, w.fb_rows, w.fb_count, st);
+  return score_topk_fallback(d, w.fb_users, w.fb_rows, w.fb_count, w.fb_scratch, w.fb_cap, st);
 }
 
 }  // namespace srb
 
+// byte offset of the int32 fallback counter inside the workspace (diagnostics: how many users the
+// exact kernel had to re-run)
+extern "C" int64_t srb_topk_fallback_count_offset(int32_t n_q, int32_t n_items) {
+  if (n_q <= 0 || n_items <= 0) return -1;
+  const srb::TcWorkspace w = srb::tc_carve((char*)256, n_q, n_items);
+  return (int64_t)((char*)w.fb_count - (char*)256);
+}
+
 extern "C" int64_t srb_topk_workspace_bytes(int32_t n_q, int32_t n_items, int32_t d, int32_t k) {
-  (void)n_items;
   (void)d;
   (void)k;
-  if (n_q <= 0) return 0;
-  return srb::tc_carve(nullptr, n_q).bytes;
+  if (n_q <= 0 || n_items <= 0) return 0;
+  return srb::tc_carve(nullptr, n_q, n_items).bytes;
 }

@@ -42,6 +42,104 @@ struct SpmmArgs {
   float* peer_p[8];    // updated parameters (Adam epilogue) -> every rank's copy
 };
 
+// Epilogue of one output row held by a lane group (gl = lane within the group): dense addend, noise,
+// store / peer pushes, running layer sum, Adam.  All lanes of the warp must call it (shuffles);
+// `valid` gates the memory traffic.
+template <int D>
+__device__ __forceinline__ void spmm_epilogue(const SpmmArgs& a, int row, int gl, float4 acc0, float4 acc1, bool valid) {
+  constexpr int LPR = D / 8;
+  constexpr int HALF = D / 2;
+  {
+    // ---- epilogue (per lane group = per row) ----
+    const size_t off = (size_t)(a.row_begin + row) * D + gl * 4;
+    float4 y0 = acc0, y1 = acc1;
+    if (a.extra && valid) {
+      y0 = f4_fma(a.extra_scale, *reinterpret_cast<const float4*>(a.extra + off), y0);
+      y1 = f4_fma(a.extra_scale, *reinterpret_cast<const float4*>(a.extra + off + HALF), y1);
+    }
+    if (a.noise_mode) {
+      float4 n0 = f4_zero(), n1 = f4_zero();
+      if (a.noise_mode == 1) {
+        if (valid) {
+          n0 = ldg4(a.noise + off);
+          n1 = ldg4(a.noise + off + HALF);
+        }
+      } else {
+        const uint32_t stp = a.pstep ? (uint32_t)*a.pstep : 0u;
+        const uint32_t grow = (uint32_t)(a.row_begin + row);
+        const uint4 r0 = philox4x32_10(make_uint4(grow, (uint32_t)gl, a.poff.x, a.poff.y ^ stp), a.pkey);
+        const uint4 r1 = philox4x32_10(make_uint4(grow, (uint32_t)(gl + LPR), a.poff.x, a.poff.y ^ stp), a.pkey);
+        n0 = make_float4(u32_to_unit(r0.x), u32_to_unit(r0.y), u32_to_unit(r0.z), u32_to_unit(r0.w));
+        n1 = make_float4(u32_to_unit(r1.x), u32_to_unit(r1.y), u32_to_unit(r1.z), u32_to_unit(r1.w));
+      }
+      float ss = f4_dot(n0, n0) + f4_dot(n1, n1);
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(SRB_FULL_MASK, ss, o);
+      const float nrm = fmaxf(sqrtf(ss), 1e-12f);  // F.normalize eps
+#define SRB_PERT(Y, N, F) Y.F += sgnf(Y.F) * (N.F / nrm) * a.eps;
+      SRB_PERT(y0, n0, x) SRB_PERT(y0, n0, y) SRB_PERT(y0, n0, z) SRB_PERT(y0, n0, w)
+      SRB_PERT(y1, n1, x) SRB_PERT(y1, n1, y) SRB_PERT(y1, n1, z) SRB_PERT(y1, n1, w)
+#undef SRB_PERT
+    }
+    if (!valid) return;
+    if (a.Y) {
+      st4(a.Y + off, y0);
+      st4(a.Y + off + HALF, y1);
+    }
+    if (a.world > 0 && a.peer[0]) {  // fused all-gather: NVLink P2P stores into every rank's layer buffer
+#pragma unroll 1
+      for (int g = 0; g < a.world; ++g) {
+        st4(a.peer[g] + off, y0);
+        st4(a.peer[g] + off + HALF, y1);
+      }
+    }
+    if (a.sum_out) {
+      float4 s0 = y0, s1 = y1;
+      if (a.sum_in) {
+        s0 = f4_add(s0, *reinterpret_cast<const float4*>(a.sum_in + off));
+        s1 = f4_add(s1, *reinterpret_cast<const float4*>(a.sum_in + off + HALF));
+      }
+      s0 = f4_scale(a.sum_scale, s0);
+      s1 = f4_scale(a.sum_scale, s1);
+      st4(a.sum_out + off, s0);
+      st4(a.sum_out + off + HALF, s1);
+      if (a.world > 0 && a.peer_sum[0]) {
+#pragma unroll 1
+        for (int g = 0; g < a.world; ++g) {
+          st4(a.peer_sum[g] + off, s0);
+          st4(a.peer_sum[g] + off + HALF, s1);
+        }
+      }
+    }
+    if (a.ap) {
+      const float step_size = a.ascal[0];
+      const float bc2_sqrt = a.ascal[1];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const size_t o2 = off + h * HALF;
+        const float4 g = h ? y1 : y0;
+        float4 p4 = *reinterpret_cast<const float4*>(a.ap + o2);
+        float4 m = *reinterpret_cast<const float4*>(a.am + o2);
+        float4 v4 = *reinterpret_cast<const float4*>(a.av + o2);
+#define SRB_ADAM1(F)                                          \
+  m.F = m.F + a.w1 * (g.F - m.F);                             \
+  v4.F = v4.F * a.b2;                                         \
+  v4.F = v4.F + (a.w2 * g.F) * g.F;                           \
+  p4.F = p4.F - step_size * (m.F / (sqrtf(v4.F) / bc2_sqrt + a.aeps));
+        SRB_ADAM1(x) SRB_ADAM1(y) SRB_ADAM1(z) SRB_ADAM1(w)
+#undef SRB_ADAM1
+        st4(a.ap + o2, p4);
+        st4(a.am + o2, m);
+        st4(a.av + o2, v4);
+        if (a.world > 0 && a.peer_p[0]) {
+#pragma unroll 1
+          for (int g = 0; g < a.world; ++g) st4(a.peer_p[g] + o2, p4);
+        }
+      }
+    }
+  }
+}
+
 // Mapping: a row vector of D floats lives on LPR = D/8 lanes (two float4 per lane: columns
 // [4*gl, 4*gl+4) and [D/2 + 4*gl, ...)).  Rows are taken in `row_order` (degree-descending):
 //   * the first n_long rows (degree >= the host's threshold) get a whole warp each: the 32/LPR lane
@@ -132,93 +230,7 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmArgs a) {
       }
       valid = valid && grp == 0;
     }
-    // ---- epilogue (per lane group = per row) ----
-    const size_t off = (size_t)(a.row_begin + row) * D + gl * 4;
-    float4 y0 = acc0, y1 = acc1;
-    if (a.extra && valid) {
-      y0 = f4_fma(a.extra_scale, *reinterpret_cast<const float4*>(a.extra + off), y0);
-      y1 = f4_fma(a.extra_scale, *reinterpret_cast<const float4*>(a.extra + off + HALF), y1);
-    }
-    if (a.noise_mode) {
-      float4 n0 = f4_zero(), n1 = f4_zero();
-      if (a.noise_mode == 1) {
-        if (valid) {
-          n0 = ldg4(a.noise + off);
-          n1 = ldg4(a.noise + off + HALF);
-        }
-      } else {
-        const uint32_t stp = a.pstep ? (uint32_t)*a.pstep : 0u;
-        const uint32_t grow = (uint32_t)(a.row_begin + row);
-        const uint4 r0 = philox4x32_10(make_uint4(grow, (uint32_t)gl, a.poff.x, a.poff.y ^ stp), a.pkey);
-        const uint4 r1 = philox4x32_10(make_uint4(grow, (uint32_t)(gl + LPR), a.poff.x, a.poff.y ^ stp), a.pkey);
-        n0 = make_float4(u32_to_unit(r0.x), u32_to_unit(r0.y), u32_to_unit(r0.z), u32_to_unit(r0.w));
-        n1 = make_float4(u32_to_unit(r1.x), u32_to_unit(r1.y), u32_to_unit(r1.z), u32_to_unit(r1.w));
-      }
-      float ss = f4_dot(n0, n0) + f4_dot(n1, n1);
-#pragma unroll
-      for (int o = LPR / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(SRB_FULL_MASK, ss, o);
-      const float nrm = fmaxf(sqrtf(ss), 1e-12f);  // F.normalize eps
-#define SRB_PERT(Y, N, F) Y.F += sgnf(Y.F) * (N.F / nrm) * a.eps;
-      SRB_PERT(y0, n0, x) SRB_PERT(y0, n0, y) SRB_PERT(y0, n0, z) SRB_PERT(y0, n0, w)
-      SRB_PERT(y1, n1, x) SRB_PERT(y1, n1, y) SRB_PERT(y1, n1, z) SRB_PERT(y1, n1, w)
-#undef SRB_PERT
-    }
-    if (!valid) continue;
-    if (a.Y) {
-      st4(a.Y + off, y0);
-      st4(a.Y + off + HALF, y1);
-    }
-    if (a.world > 0 && a.peer[0]) {  // fused all-gather: NVLink P2P stores into every rank's layer buffer
-#pragma unroll 1
-      for (int g = 0; g < a.world; ++g) {
-        st4(a.peer[g] + off, y0);
-        st4(a.peer[g] + off + HALF, y1);
-      }
-    }
-    if (a.sum_out) {
-      float4 s0 = y0, s1 = y1;
-      if (a.sum_in) {
-        s0 = f4_add(s0, *reinterpret_cast<const float4*>(a.sum_in + off));
-        s1 = f4_add(s1, *reinterpret_cast<const float4*>(a.sum_in + off + HALF));
-      }
-      s0 = f4_scale(a.sum_scale, s0);
-      s1 = f4_scale(a.sum_scale, s1);
-      st4(a.sum_out + off, s0);
-      st4(a.sum_out + off + HALF, s1);
-      if (a.world > 0 && a.peer_sum[0]) {
-#pragma unroll 1
-        for (int g = 0; g < a.world; ++g) {
-          st4(a.peer_sum[g] + off, s0);
-          st4(a.peer_sum[g] + off + HALF, s1);
-        }
-      }
-    }
-    if (a.ap) {
-      const float step_size = a.ascal[0];
-      const float bc2_sqrt = a.ascal[1];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const size_t o2 = off + h * HALF;
-        const float4 g = h ? y1 : y0;
-        float4 p4 = *reinterpret_cast<const float4*>(a.ap + o2);
-        float4 m = *reinterpret_cast<const float4*>(a.am + o2);
-        float4 v4 = *reinterpret_cast<const float4*>(a.av + o2);
-#define SRB_ADAM1(F)                                          \
-  m.F = m.F + a.w1 * (g.F - m.F);                             \
-  v4.F = v4.F * a.b2;                                         \
-  v4.F = v4.F + (a.w2 * g.F) * g.F;                           \
-  p4.F = p4.F - step_size * (m.F / (sqrtf(v4.F) / bc2_sqrt + a.aeps));
-        SRB_ADAM1(x) SRB_ADAM1(y) SRB_ADAM1(z) SRB_ADAM1(w)
-#undef SRB_ADAM1
-        st4(a.ap + o2, p4);
-        st4(a.am + o2, m);
-        st4(a.av + o2, v4);
-        if (a.world > 0 && a.peer_p[0]) {
-#pragma unroll 1
-          for (int g = 0; g < a.world; ++g) st4(a.peer_p[g] + o2, p4);
-        }
-      }
-    }
+    spmm_epilogue<D>(a, row, gl, acc0, acc1, valid);
   }
 }
 

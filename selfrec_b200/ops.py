@@ -348,8 +348,9 @@ def InfoNCE(view1, view2, temperature, b_cos=True):
 # ----------------------------------------------------------------------------------------
 # scoring + top-k
 # ----------------------------------------------------------------------------------------
-def score_topk(user_emb, item_emb, users, rated_ptr, rated_idx, k, impl=0):
-    """ids [n_q, k] int32, scores [n_q, k] fp32 for the listed users (masked, score-descending)."""
+def score_topk(user_emb, item_emb, users, rated_ptr, rated_idx, k, impl=0, stats=None):
+    """ids [n_q, k] int32, scores [n_q, k] fp32 for the listed users (masked, score-descending).
+    stats: optional dict; impl 2 stores the fallback-counter tensor view under "fallback_count"."""
     lib = _lib.require_device()
     user_emb, item_emb = _f32c(user_emb, "score user_emb"), _f32c(item_emb, "score item_emb")
     dev = user_emb.device
@@ -373,6 +374,9 @@ def score_topk(user_emb, item_emb, users, rated_ptr, rated_idx, k, impl=0):
         ws = torch.empty(max(nb, 16), device=dev, dtype=torch.uint8)
         desc.workspace, desc.workspace_bytes = _p(ws), nb
     _lib.check(lib.srb_score_topk(C.byref(desc), _stream()), "srb_score_topk")
+    if stats is not None and impl == 2 and n_q > 0:
+        off = lib.srb_topk_fallback_count_offset(n_q, item_emb.shape[0])
+        stats["fallback_count"] = ws[off:off + 4].view(torch.int32)
     return out_ids, out_sc
 
 
