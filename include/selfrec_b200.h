@@ -57,9 +57,11 @@ typedef struct srb_spmm_desc {
   int32_t n_cols;
   int32_t d;
   /* optional processing order of rows (length n_rows), NULL = natural order; when it is sorted by
-   * descending degree, the first n_long_rows entries (long rows) are given a whole warp each */
+   * descending degree, the first n_vlong_rows entries are given a whole CTA each and the next
+   * n_long_rows entries a whole warp each (the rest share warps) */
   const int32_t* row_order;
   int32_t n_long_rows;
+  int32_t n_vlong_rows;
   const float* X;     /* [n_cols, d] */
   float* Y;           /* [n_rows, d] or NULL (result only feeds sum/adam) */
   const float* extra; /* optional dense addend [n_rows, d]: y += extra_scale * extra[row] */
@@ -98,6 +100,7 @@ typedef struct srb_encoder_desc {
   const float* vals;
   const int32_t* row_order;
   int32_t n_long_rows;
+  int32_t n_vlong_rows;
   int32_t n;
   int32_t d;
   int32_t n_layers;
@@ -109,6 +112,13 @@ typedef struct srb_encoder_desc {
   uint64_t philox_seed;
   uint64_t philox_offset;
   const int32_t* philox_step_dev;
+  /* optional: the LAST layer is only evaluated for these rows (device list, duplicates allowed), e.g.
+   * the batch rows of a training step -- nothing else reads the final mean there */
+  const int32_t* last_rows;
+  int32_t n_last_rows;
+  float* last_rows_out; /* [n, d], required with last_rows: receives the final mean of the listed rows
+                           (final_out then only holds the running sum; the list may contain duplicates,
+                           so the last layer must not update the running sum in place) */
   const float* E0; /* [n, d] parameters */
   float* final_out; /* [n, d] */
   float* cl_out;    /* [n, d] or NULL */
@@ -287,6 +297,7 @@ typedef struct srb_graph_csr {
   const float* vals;
   const int32_t* row_order;
   int32_t n_long_rows;
+  int32_t n_vlong_rows;
 } srb_graph_csr;
 
 typedef struct srb_step_desc {

@@ -25,6 +25,7 @@ struct Ws {
   float* acc0;
   float* acc1;
   float* gd;      // dense gradient accumulator / last-layer addend
+  float* rsum;    // running layer sum of the encoder being evaluated (training forwards)
   float* g_emb;   // [3,B,d]
   float* g_l2;    // [3,B,d]
   float* g_nce;   // 4 x [2B,d]
@@ -33,6 +34,7 @@ struct Ws {
   float* nce_losses;   // [4]
   int32_t* idx_cat;    // [2B] SGL concatenated unique ids
   int32_t* n_cat;      // [1]
+  int32_t* batch_rows; // [3B] table rows of the batch (u, U+i, U+j), padded with the first entry
   void* nce_ws;
   int64_t nce_ws_bytes;
 };
@@ -59,6 +61,7 @@ static int64_t carve(const srb_step_desc* s, Ws* w, char* base) {
   float* f_a0 = (float*)take(nd);
   float* f_a1 = (float*)take(graph ? nd : 0);
   float* f_gd = (float*)take(graph ? nd : 0);
+  float* f_rsum = (float*)take(graph ? nd : 0);
   float* f_gemb = (float*)take(3 * B * d * 4);
   float* f_gl2 = (float*)take(3 * B * d * 4);
   float* f_gnce = (float*)take(has_cl ? 4 * 2 * B * d * 4 : 0);
@@ -67,6 +70,7 @@ static int64_t carve(const srb_step_desc* s, Ws* w, char* base) {
   float* f_nl = (float*)take(4 * 4);
   int32_t* i_cat = (int32_t*)take(2 * B * 4);
   int32_t* i_ncat = (int32_t*)take(4);
+  int32_t* i_brows = (int32_t*)take(3 * B * 4);
   const int64_t nws = has_cl ? srb_infonce_workspace_bytes((int32_t)(2 * B), (int32_t)d, 2) : 0;
   void* v_nws = take(nws);
   if (w) {
@@ -78,6 +82,7 @@ static int64_t carve(const srb_step_desc* s, Ws* w, char* base) {
     w->acc0 = f_a0;
     w->acc1 = f_a1;
     w->gd = f_gd;
+    w->rsum = f_rsum;
     w->g_emb = f_gemb;
     w->g_l2 = f_gl2;
     w->g_nce = f_gnce;
@@ -86,6 +91,7 @@ static int64_t carve(const srb_step_desc* s, Ws* w, char* base) {
     w->nce_losses = f_nl;
     w->idx_cat = i_cat;
     w->n_cat = i_ncat;
+    w->batch_rows = i_brows;
     w->nce_ws = v_nws;
     w->nce_ws_bytes = nws;
   }
@@ -100,6 +106,17 @@ __global__ void build_cat_idx_kernel(const int32_t* batch, int cap, int n_users,
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nu + ni; t += gridDim.x * blockDim.x)
     idx_cat[t] = (t < nu) ? uu[t] : n_users + ui[t - nu];
   if (blockIdx.x == 0 && threadIdx.x == 0) *n_cat = nu + ni;
+}
+
+// rows of the [N, d] tables a batch touches: u, U + i, U + j (entries past the batch repeat row u[0])
+__global__ void build_batch_rows_kernel(const int32_t* batch, int cap, int n_users, int32_t* rows) {
+  const int b = min(batch[0], cap);
+  const int32_t* u = batch + SRB_BATCH_HEADER;
+  const int first = (b > 0) ? u[0] : 0;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < 3 * cap; t += gridDim.x * blockDim.x) {
+    const int sec = t / cap, k = t % cap;
+    rows[t] = (k < b) ? (sec == 0 ? u[k] : n_users + u[sec * cap + k]) : first;
+  }
 }
 
 __global__ void finalize_losses_kernel(const float* bpr_losses, const float* nce_losses, int n_nce, float cl_rate, float* out) {
@@ -129,6 +146,7 @@ static int spmm_simple(const srb_step_desc* s, const srb_graph_csr* g, const flo
   p.vals = g->vals;
   p.row_order = g->row_order;
   p.n_long_rows = g->n_long_rows;
+  p.n_vlong_rows = g->n_vlong_rows;
   p.n_rows = p.n_cols = s->n_users + s->n_items;
   p.d = s->d;
   p.X = x;
@@ -187,12 +205,14 @@ static ScatterSeg seg(const float* src, const int32_t* rows, const int32_t* n_de
 
 static int encoder(const srb_step_desc* s, const Ws& w, const srb_graph_csr* g, bool include_ego, int noise_mode, int view,
                    int layer_cl, float* final_out, float* cl_out, cudaStream_t st) {
+  // training forward: the final mean is only read at the batch rows, so the last layer skips the rest
   srb_encoder_desc e = {};
   e.rowptr = g->rowptr;
   e.colidx = g->colidx;
   e.vals = g->vals;
   e.row_order = g->row_order;
   e.n_long_rows = g->n_long_rows;
+  e.n_vlong_rows = g->n_vlong_rows;
   e.n = s->n_users + s->n_items;
   e.d = s->d;
   e.n_layers = s->n_layers;
@@ -205,7 +225,14 @@ static int encoder(const srb_step_desc* s, const Ws& w, const srb_graph_csr* g, 
   e.philox_offset = ((uint64_t)view << 32) | 0x10u;
   e.philox_step_dev = s->step_dev;
   e.E0 = s->params;
-  e.final_out = final_out;
+  if (cl_out && layer_cl == s->n_layers) {
+    e.final_out = final_out;  // the last layer is the CL view and is needed in full
+  } else {
+    e.last_rows = w.batch_rows;
+    e.n_last_rows = 3 * s->batch_cap;
+    e.last_rows_out = final_out;  // batch rows of the mean land here; the running sum lives in w.rsum
+    e.final_out = w.rsum;
+  }
   e.cl_out = cl_out;
   e.work0 = w.work0;
   e.work1 = w.work1;
@@ -255,6 +282,10 @@ extern "C" int srb_train_step(const srb_step_desc* s, void* stream) {
   SRB_TRY(srb_adam_prepare(s->step_dev, s->scalars, s->lr, s->beta1, s->beta2, stream));
 
   // ---- forward ----
+  if (s->model != SRB_MODEL_MF) {
+    build_batch_rows_kernel<<<(3 * B + 255) / 256, 256, 0, st>>>(s->batch, B, U, w.batch_rows);
+    SRB_TRY(post_launch("build_batch_rows_kernel"));
+  }
   const float* table = s->params;  // table BPR gathers from
   int n_nce = 0;
   switch (s->model) {

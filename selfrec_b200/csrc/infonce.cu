@@ -47,6 +47,7 @@ struct NceProblem {
   float* dV1;  // [NP][D]
   float* dV2;
   float* loss_acc;  // [1]
+  float* lse;       // [NP] (tensor-core path)
 };
 
 struct NceArgs {
@@ -408,9 +409,38 @@ static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * 
 static inline int nce_np(int n) { return (int)align_up(n > 0 ? n : 1, 128); }  // 128: tile edge of the tensor-core path
 
 static int64_t nce_problem_floats(int np, int d) {
-  // V1 V2 V1T V2T dV1 dV2 + TF32-rounded V1 V2 V1T V2T: 10 * np * d ; inv1 inv2 diag: 3 * np ;
+  // V1 V2 V1T V2T dV1 dV2 + TF32 hi and lo parts of V1 V2 V1T V2T: 14 * np * d ; inv1 inv2 diag: 3 * np ;
   // part_m part_l: 2 * splits * np ; loss_acc (padded)
-  return 10ll * np * d + 3ll * np + 2ll * NCE_MAX_SPLITS * np + 64;
+  return 14ll * np * d + 4ll * np + 2ll * NCE_MAX_SPLITS * np + 64;  // + lse[np]
+}
+
+// finish for the tensor-core path: dVhat = D + (P_ii - 1) * w/(n tau) * vhat_other (exact fp32), then the
+// same normalisation backward as nce_finish_kernel
+__global__ void __launch_bounds__(256) nce_tc_finish_kernel(const NceArgs a) {
+  constexpr int D = 64;
+  const NceProblem& p = a.p[blockIdx.y];
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int n = nce_n(p);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *p.loss = (n > 0) ? *p.loss_acc / (float)n : 0.f;
+  if (i >= n) return;
+  const float pii = expf(p.diag[i] - p.lse[i]);
+  const float cd = (pii - 1.f) * p.weight * a.inv_tau / (float)n;
+  const float2 v1 = *reinterpret_cast<const float2*>(p.V1 + (size_t)i * D + lane * 2);
+  const float2 v2 = *reinterpret_cast<const float2*>(p.V2 + (size_t)i * D + lane * 2);
+#pragma unroll 1
+  for (int side = 0; side < 2; ++side) {
+    const float2 vh = side ? v2 : v1;
+    const float2 vo = side ? v1 : v2;
+    float2 dv = *reinterpret_cast<const float2*>((side ? p.dV2 : p.dV1) + (size_t)i * D + lane * 2);
+    dv.x = fmaf(cd, vo.x, dv.x);
+    dv.y = fmaf(cd, vo.y, dv.y);
+    const float dot = warp_sum(vh.x * dv.x + vh.y * dv.y);
+    const float inv = side ? p.inv2[i] : p.inv1[i];
+    float2 o = dv;
+    if (a.b_cos) o = make_float2((dv.x - vh.x * dot) * inv, (dv.y - vh.y * dot) * inv);
+    *reinterpret_cast<float2*>((side ? p.g2 : p.g1) + (size_t)i * D + lane * 2) = o;
+  }
 }
 
 // 0 = auto (tensor cores when d == 64), 1 = CUDA-core tiles, 2 = tensor cores
@@ -423,10 +453,14 @@ static int nce_impl() {
   return impl;
 }
 
-__global__ void __launch_bounds__(256) nce_round_kernel(const float* __restrict__ src, float* __restrict__ dst, long long n4) {
+// x = hi + lo with hi = rna_tf32(x), lo = rna_tf32(x - hi)   ("3xTF32" operand split)
+__global__ void __launch_bounds__(256) nce_split_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo,
+                                                       long long n4) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 v = reinterpret_cast<const float4*>(src)[i];
-    reinterpret_cast<float4*>(dst)[i] = make_float4(to_tf32_rna(v.x), to_tf32_rna(v.y), to_tf32_rna(v.z), to_tf32_rna(v.w));
+    const float4 h = make_float4(to_tf32_rna(v.x), to_tf32_rna(v.y), to_tf32_rna(v.z), to_tf32_rna(v.w));
+    reinterpret_cast<float4*>(hi)[i] = h;
+    reinterpret_cast<float4*>(lo)[i] = make_float4(to_tf32_rna(v.x - h.x), to_tf32_rna(v.y - h.y), to_tf32_rna(v.z - h.z), to_tf32_rna(v.w - h.w));
   }
 }
 
@@ -444,7 +478,8 @@ static int nce_launch_tc(const NceArgs& a, int n_problems, cudaStream_t st) {
   t.np = np;
   t.inv_tau = a.inv_tau;
   const int row_blocks = np / NT_T;
-  int splits = (2 * sm_count() + row_blocks * n_problems - 1) / (row_blocks * n_problems);
+  // one CTA per SM (224 KB of shared memory each): as many column splits as fit in a single wave
+  int splits = sm_count() / (row_blocks * n_problems);
   if (splits < 1) splits = 1;
   if (splits > NT_MAX_SPLITS) splits = NT_MAX_SPLITS;
   if (splits > row_blocks) splits = row_blocks;
@@ -452,15 +487,21 @@ static int nce_launch_tc(const NceArgs& a, int n_problems, cudaStream_t st) {
   const long long nd = (long long)np * d;
   for (int q = 0; q < n_problems; ++q) {
     const NceProblem& p = a.p[q];
-    // rounded copies live behind dV2: V1R V2R V1TR V2TR
-    float* r = p.dV2 + nd;
-    nce_round_kernel<<<64, 256, 0, st>>>(p.V1, r, 4 * nd / 4);  // V1 V2 V1T V2T are contiguous
-    SRB_TRY(post_launch("nce_round_kernel"));
-    SRB_REQUIRE(make_tmap_f32_rows(&maps.v1[q], r, (uint64_t)np, d, NT_T) == 0 &&
-                    make_tmap_f32_rows(&maps.v2[q], r + nd, (uint64_t)np, d, NT_T) == 0 &&
-                    make_tmap_f32_rows(&maps.v1t[q], r + 2 * nd, (uint64_t)d, (uint64_t)np, NT_D) == 0 &&
-                    make_tmap_f32_rows(&maps.v2t[q], r + 3 * nd, (uint64_t)d, (uint64_t)np, NT_D) == 0,
-                "infonce: cuTensorMapEncodeTiled failed");
+    // hi / lo parts live behind dV2: hi of (V1 V2 V1T V2T) then lo of the same four
+    float* hi = p.dV2 + nd;
+    float* lo = hi + 4 * nd;
+    nce_split_kernel<<<128, 256, 0, st>>>(p.V1, hi, lo, 4 * nd / 4);  // V1 V2 V1T V2T are contiguous
+    SRB_TRY(post_launch("nce_split_kernel"));
+    for (int h = 0; h < 2; ++h) {
+      float* r = h ? lo : hi;
+      SRB_REQUIRE(make_tmap_f32_rows(&maps.v1r[q][h], r, (uint64_t)np, d, NT_T) == 0 &&
+                      make_tmap_f32_rows(&maps.v2r[q][h], r + nd, (uint64_t)np, d, NT_T) == 0 &&
+                      make_tmap_f32_rows(&maps.v1c[q][h], r, (uint64_t)np, d, NT_C) == 0 &&
+                      make_tmap_f32_rows(&maps.v2c[q][h], r + nd, (uint64_t)np, d, NT_C) == 0 &&
+                      make_tmap_f32_rows(&maps.v1t[q][h], r + 2 * nd, (uint64_t)d, (uint64_t)np, NT_D) == 0 &&
+                      make_tmap_f32_rows(&maps.v2t[q][h], r + 3 * nd, (uint64_t)d, (uint64_t)np, NT_D) == 0,
+                  "infonce: cuTensorMapEncodeTiled failed");
+    }
     NtProblem& o = t.p[q];
     o.n = p.n;
     o.n_dev = p.n_dev;
@@ -468,15 +509,20 @@ static int nce_launch_tc(const NceArgs& a, int n_problems, cudaStream_t st) {
     o.diag = p.diag;
     o.part_m = p.part_m;
     o.part_l = p.part_l;
+    o.lse = p.lse;
     o.dV1 = p.dV1;
     o.dV2 = p.dV2;
     o.loss_acc = p.loss_acc;
   }
-  for (int q = n_problems; q < 4; ++q) {
-    maps.v1[q] = maps.v1[0];
-    maps.v2[q] = maps.v2[0];
-    maps.v1t[q] = maps.v1t[0];
-    maps.v2t[q] = maps.v2t[0];
+  for (int q = n_problems; q < 2; ++q) {
+    for (int h = 0; h < 2; ++h) {
+      maps.v1r[q][h] = maps.v1r[0][h];
+      maps.v2r[q][h] = maps.v2r[0][h];
+      maps.v1c[q][h] = maps.v1c[0][h];
+      maps.v2c[q][h] = maps.v2c[0][h];
+      maps.v1t[q][h] = maps.v1t[0][h];
+      maps.v2t[q][h] = maps.v2t[0][h];
+    }
     t.p[q] = t.p[0];
   }
   const size_t smem = NtSmem::total + 1024;
@@ -496,8 +542,8 @@ static int nce_launch_tc(const NceArgs& a, int n_problems, cudaStream_t st) {
   SRB_TRY(post_launch("nce_tc_kernel<grad_b>"));
   {
     dim3 g2((np + 7) / 8, n_problems);
-    nce_finish_kernel<64><<<g2, 256, 0, st>>>(a);
-    SRB_TRY(post_launch("nce_finish_kernel"));
+    nce_tc_finish_kernel<<<g2, 256, 0, st>>>(a);
+    SRB_TRY(post_launch("nce_tc_finish_kernel"));
   }
   return SRB_OK;
 }
@@ -596,17 +642,18 @@ extern "C" int srb_infonce_fwd_bwd(const srb_infonce_desc* d, void* stream) {
     p.V2T = base + 3 * nd;
     p.dV1 = base + 4 * nd;
     p.dV2 = base + 5 * nd;
-    float* t = base + 10 * nd;  // [6 nd, 10 nd): TF32-rounded copies (tensor-core path)
+    float* t = base + 14 * nd;  // [6 nd, 14 nd): TF32 hi / lo parts (tensor-core path)
     p.inv1 = t;
     p.inv2 = t + a.np;
     p.diag = t + 2 * a.np;
     p.part_m = t + 3 * a.np;
     p.part_l = t + 3 * a.np + (int64_t)srb::NCE_MAX_SPLITS * a.np;
-    p.loss_acc = t + 3 * a.np + 2ll * srb::NCE_MAX_SPLITS * a.np;
+    p.lse = t + 3 * a.np + 2ll * srb::NCE_MAX_SPLITS * a.np;
+    p.loss_acc = p.lse + a.np;
   }
   cudaStream_t st = (cudaStream_t)stream;
   const int impl = srb::nce_impl();
-  if (d->d == 64 && d->b_cos && impl != 1) return srb::nce_launch_tc(a, d->n_problems, st);
+  if (d->d == 64 && d->b_cos && impl != 1 && d->n_problems <= 2) return srb::nce_launch_tc(a, d->n_problems, st);
   SRB_REQUIRE(impl != 2, "infonce: SRB_NCE_IMPL=2 (tensor cores) needs d == 64 and b_cos");
   switch (d->d) {
     case 32: return srb::nce_launch<32>(a, d->n_problems, st);

@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(256) score_topk_kernel(const TopkArgs a) {
   float ls[4];
   int li[4];
   int cur[4], cend[4];
+  int ev[4];  // lane l holds rated_idx[cur + l] of user r (reloaded only when the cursor moves)
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
     ls[r] = -INFINITY;
@@ -74,6 +75,7 @@ __global__ void __launch_bounds__(256) score_topk_kernel(const TopkArgs a) {
     } else {
       cur[r] = cend[r] = 0;
     }
+    ev[r] = (cur[r] + lane < cend[r]) ? a.rated_idx[cur[r] + lane] : 0x7fffffff;
   }
   const int K = a.k;
 
@@ -114,12 +116,11 @@ __global__ void __launch_bounds__(256) score_topk_kernel(const TopkArgs a) {
         if (n0 + lane + 32 * c >= a.n_items) s[r][c] = -INFINITY;
       // rated-item mask: walk this user's sorted rated list through the tile
       while (true) {
-        const int pos = cur[r] + lane;
-        int e = (pos < cend[r]) ? a.rated_idx[pos] : 0x7fffffff;
-        const unsigned in = __ballot_sync(SRB_FULL_MASK, e < n0 + TK_TN);
+        const unsigned in = __ballot_sync(SRB_FULL_MASK, ev[r] < n0 + TK_TN);
         const int cnt = __popc(in);
+        if (cnt == 0) break;
         for (int t = 0; t < cnt; ++t) {
-          const int et = __shfl_sync(SRB_FULL_MASK, e, t) - n0;
+          const int et = __shfl_sync(SRB_FULL_MASK, ev[r], t) - n0;
           if (et >= 0 && (et & 31) == lane) {
             const int c = et >> 5;
 #pragma unroll
@@ -128,6 +129,7 @@ __global__ void __launch_bounds__(256) score_topk_kernel(const TopkArgs a) {
           }
         }
         cur[r] += cnt;
+        ev[r] = (cur[r] + lane < cend[r]) ? a.rated_idx[cur[r] + lane] : 0x7fffffff;
         if (cnt < 32) break;
       }
       // sequential (id-ordered) insertion, 32 candidates per round

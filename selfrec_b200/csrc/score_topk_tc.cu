@@ -14,7 +14,7 @@
 //                                  (2 stages x 2 halves x 128 columns = all 512 columns)
 //            warps 2-9 epilogue  : tcgen05.ld (lane = user row, next group's load in flight while one
 //                                  is processed), rated-item cursor, per-thread top-32 candidate
-//                                  min-heap in shared memory
+//                                  list (4 buckets of 8, minima in registers) in shared memory
 //          The raw fp32 tables are fed to the tensor core, which reads them as TF32 (low 13
 //          mantissa bits ignored): scores carry <= 2^-9 ||u|| ||i|| error -- candidates only.
 // Stage 3  tc_rescore_kernel    warp per user: exact fp32 fma-chain scores of the 32 candidates
@@ -181,14 +181,21 @@ tc_score_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_const
     int32_t* ci = reinterpret_cast<int32_t*>(sm + TcSmem::cand_i_off);
     float thr = -INFINITY;
     int cnt = 0;
-    int cur = 0, cend = 0, next_rated = 0x7fffffff;
+    // cursor into this user's sorted rated list; the id after next is prefetched so that advancing the
+    // cursor never makes the warp wait for a global load
+    int cur = 0, cend = 0, next_rated = 0x7fffffff, after_next = 0x7fffffff;
     if (active && a.rated_ptr) {
       const int u = a.users[q];
       cur = a.rated_ptr[u];
       cend = a.rated_ptr[u + 1];
       if (cur < cend) next_rated = a.rated_idx[cur];
+      if (cur + 1 < cend) after_next = a.rated_idx[cur + 1];
     }
-    // candidate list = min-heap of 32 (score, id) in shared memory, column `tix`; thr = heap root
+    // candidate list: 32 (score, id) slots in shared memory (column `tix`), organised as 4 buckets of 8.
+    // Registers keep each bucket's minimum and its slot, so replacing the global minimum re-scans only
+    // one bucket (8 independent shared-memory loads) instead of the whole list.
+    float bm0 = INFINITY, bm1 = INFINITY, bm2 = INFINITY, bm3 = INFINITY;  // bucket minima (valid once full)
+    int bp0 = 0, bp1 = 8, bp2 = 16, bp3 = 24;                              // slot of each bucket's minimum
     auto process_group = [&](const uint32_t (&r)[32], int g0) {
       uint32_t mask = 0;
 #pragma unroll
@@ -199,7 +206,8 @@ tc_score_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_const
       while (next_rated < g0 + 32) {
         if (next_rated >= g0) mask &= ~(1u << (next_rated - g0));
         ++cur;
-        next_rated = (cur < cend) ? a.rated_idx[cur] : 0x7fffffff;
+        next_rated = after_next;
+        after_next = (cur + 1 < cend) ? a.rated_idx[cur + 1] : 0x7fffffff;
       }
       while (mask) {
         const int j = __ffs(mask) - 1;
@@ -211,40 +219,46 @@ tc_score_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_const
         if (!(sc > thr)) continue;  // thr may have risen inside this group
         const int id = g0 + j;
         if (cnt < TC_CAND) {
-          // filling: sift up
-          int pos = cnt++;
-          while (pos > 0) {
-            const int par = (pos - 1) >> 1;
-            const float pv = cs[par * 256 + tix];
-            if (!(sc < pv)) break;
-            cs[pos * 256 + tix] = pv;
-            ci[pos * 256 + tix] = ci[par * 256 + tix];
-            pos = par;
-          }
-          cs[pos * 256 + tix] = sc;
-          ci[pos * 256 + tix] = id;
-          if (cnt == TC_CAND) thr = cs[tix];
-        } else {
-          // replace the root (current minimum) and sift down
-          int pos = 0;
-#pragma unroll 1
-          for (;;) {
-            const int l = 2 * pos + 1;
-            if (l >= TC_CAND) break;
-            int c = l;
-            float cv = cs[l * 256 + tix];
-            if (l + 1 < TC_CAND) {
-              const float rv = cs[(l + 1) * 256 + tix];
-              if (rv < cv) cv = rv, c = l + 1;
+          cs[cnt * 256 + tix] = sc;
+          ci[cnt * 256 + tix] = id;
+          ++cnt;
+          if (cnt == TC_CAND) {  // list full: establish the bucket minima
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              float mn = INFINITY;
+              int mp = b * 8;
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float v = cs[(b * 8 + q) * 256 + tix];
+                if (v < mn) mn = v, mp = b * 8 + q;
+              }
+              if (b == 0) bm0 = mn, bp0 = mp;
+              if (b == 1) bm1 = mn, bp1 = mp;
+              if (b == 2) bm2 = mn, bp2 = mp;
+              if (b == 3) bm3 = mn, bp3 = mp;
             }
-            if (!(cv < sc)) break;
-            cs[pos * 256 + tix] = cv;
-            ci[pos * 256 + tix] = ci[c * 256 + tix];
-            pos = c;
+            thr = fminf(fminf(bm0, bm1), fminf(bm2, bm3));
           }
+        } else {
+          // evict the global minimum: it sits in the bucket whose minimum equals thr
+          int b = 3, pos = bp3;
+          if (bm2 == thr) b = 2, pos = bp2;
+          if (bm1 == thr) b = 1, pos = bp1;
+          if (bm0 == thr) b = 0, pos = bp0;
           cs[pos * 256 + tix] = sc;
           ci[pos * 256 + tix] = id;
-          thr = cs[tix];
+          float mn = INFINITY;
+          int mp = b * 8;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float v = cs[(b * 8 + q) * 256 + tix];
+            if (v < mn) mn = v, mp = b * 8 + q;
+          }
+          if (b == 0) bm0 = mn, bp0 = mp;
+          if (b == 1) bm1 = mn, bp1 = mp;
+          if (b == 2) bm2 = mn, bp2 = mp;
+          if (b == 3) bm3 = mn, bp3 = mp;
+          thr = fminf(fminf(bm0, bm1), fminf(bm2, bm3));
         }
       }
     };

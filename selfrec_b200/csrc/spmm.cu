@@ -16,7 +16,8 @@ struct SpmmArgs {
   const float* vals;
   const int32_t* row_order;
   int32_t n_rows;
-  int32_t n_long;  // leading entries of row_order that get a whole warp
+  int32_t n_vlong; // leading entries of row_order that get a whole CTA
+  int32_t n_long;  // following entries that get a whole warp
   const float* X;
   float* Y;
   const float* extra;
@@ -141,34 +142,123 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmArgs& a, int row, int gl
 }
 
 // Mapping: a row vector of D floats lives on LPR = D/8 lanes (two float4 per lane: columns
-// [4*gl, 4*gl+4) and [D/2 + 4*gl, ...)).  Rows are taken in `row_order` (degree-descending):
-//   * the first n_long rows (degree >= the host's threshold) get a whole warp each: the 32/LPR lane
-//     groups stride through the row 32 non-zeros at a time and are xor-shuffled together at the end,
-//     so the longest row costs deg/32 dependent iterations instead of deg/LPR;
-//   * the remaining rows are processed RPW = 32/LPR at a time (one per lane group; neighbours in the
+// [4*gl, 4*gl+4) and [D/2 + 4*gl, ...)).  Rows are taken in `row_order` (degree-descending), in three
+// classes so that no row is a long chain of dependent L2 round trips (~1.7 us each under load; a
+// 1600-non-zero row handled by one warp alone took as long as the rest of the matrix):
+//   * the first n_vlong rows get a whole CTA: 8 warps x 4 lane groups stride through the row, partial
+//     sums meet in shared memory;
+//   * the next n_long rows get a warp each (the 32/LPR lane groups stride 32 non-zeros per iteration
+//     and are xor-shuffled together);
+//   * the remaining rows are processed RPW = 32/LPR at a time, one per lane group (neighbours in the
 //     sorted order are equally long).
 // Each lane loads one (col, val) pair per iteration (coalesced, prefetched one iteration ahead) and
 // the pairs are walked with group-wide shuffles; every X-row gather is two 128-bit ld.global.nc per
 // lane (LPR lanes x 16 B = one contiguous half row), issued 2*SB at a time before the FMAs.
-// ~4 warp instructions per non-zero (the first version needed 18 and was issue-bound at 20 % of L2
-// throughput).
+template <int D>
+__device__ __forceinline__ void spmm_gather(const SpmmArgs& a, int p, int end, int stride, int gl, float4& acc0, float4& acc1) {
+  constexpr int LPR = D / 8;
+  constexpr int HALF = D / 2;
+  constexpr int SB = LPR < 4 ? LPR : 4;  // sub-batch: 2*SB independent 128-bit gathers per lane in flight
+  // (col, val) of the current iteration; padding slots gather row 0 with weight 0 (an L1 hit)
+  int c = 0;
+  float v = 0.f;
+  if (p + gl < end) {
+    c = __ldg(a.colidx + p + gl);
+    v = __ldg(a.vals + p + gl);
+  }
+  while (__any_sync(SRB_FULL_MASK, p < end)) {
+    int cn = 0;
+    float vn = 0.f;
+    if (p + stride + gl < end) {  // prefetch the next iteration's pair
+      cn = __ldg(a.colidx + p + stride + gl);
+      vn = __ldg(a.vals + p + stride + gl);
+    }
+#pragma unroll
+    for (int j0 = 0; j0 < LPR; j0 += SB) {
+      if (j0 > 0 && !__any_sync(SRB_FULL_MASK, p + j0 < end)) break;
+      float vv[SB];
+      float4 x0[SB], x1[SB];
+#pragma unroll
+      for (int j = 0; j < SB; ++j) {
+        const int cc = __shfl_sync(SRB_FULL_MASK, c, j0 + j, LPR);
+        vv[j] = __shfl_sync(SRB_FULL_MASK, v, j0 + j, LPR);
+        const float* xr = a.X + (size_t)cc * D + gl * 4;
+        x0[j] = ldg4(xr);
+        x1[j] = ldg4(xr + HALF);
+      }
+#pragma unroll
+      for (int j = 0; j < SB; ++j) {
+        acc0 = f4_fma(vv[j], x0[j], acc0);
+        acc1 = f4_fma(vv[j], x1[j], acc1);
+      }
+    }
+    c = cn;
+    v = vn;
+    p += stride;
+  }
+}
+
+__device__ __forceinline__ void xor_reduce_groups(float4& acc0, float4& acc1, int lpr) {
+  for (int o = lpr; o < 32; o <<= 1) {
+    acc0.x += __shfl_xor_sync(SRB_FULL_MASK, acc0.x, o);
+    acc0.y += __shfl_xor_sync(SRB_FULL_MASK, acc0.y, o);
+    acc0.z += __shfl_xor_sync(SRB_FULL_MASK, acc0.z, o);
+    acc0.w += __shfl_xor_sync(SRB_FULL_MASK, acc0.w, o);
+    acc1.x += __shfl_xor_sync(SRB_FULL_MASK, acc1.x, o);
+    acc1.y += __shfl_xor_sync(SRB_FULL_MASK, acc1.y, o);
+    acc1.z += __shfl_xor_sync(SRB_FULL_MASK, acc1.z, o);
+    acc1.w += __shfl_xor_sync(SRB_FULL_MASK, acc1.w, o);
+  }
+}
+
 template <int D>
 __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmArgs a) {
   constexpr int LPR = D / 8;     // lanes per row
   constexpr int RPW = 32 / LPR;  // rows per warp (short rows)
-  constexpr int HALF = D / 2;
-  constexpr int SB = LPR < 4 ? LPR : 4;  // sub-batch: 2*SB independent 128-bit gathers per lane in flight
   const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
   const int grp = lane / LPR;
   const int gl = lane % LPR;
   const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  const int n_long = a.n_long;
-  const int n_items = n_long + (a.n_rows - n_long + RPW - 1) / RPW;
 
+  // ---- class 1: one CTA per very long row ----
+  __shared__ float4 part[8][2][LPR];
+  for (int vr = blockIdx.x; vr < a.n_vlong; vr += gridDim.x) {
+    const int row = a.row_order ? __ldg(a.row_order + vr) : vr;
+    const int beg = __ldg(a.rowptr + row);
+    const int end = __ldg(a.rowptr + row + 1);
+    const int per = ((end - beg + 255) / 256) * 32;  // non-zeros per warp, a multiple of 32
+    const int wbeg = beg + wib * per;
+    const int wend = min(end, wbeg + per);
+    float4 acc0 = f4_zero(), acc1 = f4_zero();
+    spmm_gather<D>(a, wbeg + grp * LPR, wend, 32, gl, acc0, acc1);
+    xor_reduce_groups(acc0, acc1, LPR);
+    if (grp == 0) {
+      part[wib][0][gl] = acc0;
+      part[wib][1][gl] = acc1;
+    }
+    __syncthreads();
+    if (wib == 0) {
+      acc0 = f4_zero();
+      acc1 = f4_zero();
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        acc0 = f4_add(acc0, part[w][0][gl]);
+        acc1 = f4_add(acc1, part[w][1][gl]);
+      }
+      spmm_epilogue<D>(a, row, gl, acc0, acc1, grp == 0);
+    }
+    __syncthreads();
+  }
+
+  // ---- classes 2 and 3: one warp per long row, one lane group per short row ----
+  const int base = a.n_vlong;
+  const int n_long = a.n_long;
+  const int n_items = n_long + (a.n_rows - base - n_long + RPW - 1) / RPW;
   for (int item = warp0; item < n_items; item += nwarps) {
     const bool is_long = item < n_long;  // warp-uniform
-    const int ridx = is_long ? item : n_long + (item - n_long) * RPW + grp;
+    const int ridx = base + (is_long ? item : n_long + (item - n_long) * RPW + grp);
     bool valid = ridx < a.n_rows;
     int row = 0, p = 0, end = 0;
     if (valid) {
@@ -176,58 +266,11 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmArgs a) {
       p = __ldg(a.rowptr + row);
       end = __ldg(a.rowptr + row + 1);
     }
-    const int stride = is_long ? 32 : LPR;
     if (is_long) p += grp * LPR;
     float4 acc0 = f4_zero(), acc1 = f4_zero();
-    // (col, val) of the current iteration; padding slots gather row 0 with weight 0 (an L1 hit)
-    int c = 0;
-    float v = 0.f;
-    if (p + gl < end) {
-      c = __ldg(a.colidx + p + gl);
-      v = __ldg(a.vals + p + gl);
-    }
-    while (__any_sync(SRB_FULL_MASK, p < end)) {
-      int cn = 0;
-      float vn = 0.f;
-      if (p + stride + gl < end) {  // prefetch the next iteration's pair
-        cn = __ldg(a.colidx + p + stride + gl);
-        vn = __ldg(a.vals + p + stride + gl);
-      }
-#pragma unroll
-      for (int j0 = 0; j0 < LPR; j0 += SB) {
-        if (j0 > 0 && !__any_sync(SRB_FULL_MASK, p + j0 < end)) break;
-        float vv[SB];
-        float4 x0[SB], x1[SB];
-#pragma unroll
-        for (int j = 0; j < SB; ++j) {
-          const int cc = __shfl_sync(SRB_FULL_MASK, c, j0 + j, LPR);
-          vv[j] = __shfl_sync(SRB_FULL_MASK, v, j0 + j, LPR);
-          const float* xr = a.X + (size_t)cc * D + gl * 4;
-          x0[j] = ldg4(xr);
-          x1[j] = ldg4(xr + HALF);
-        }
-#pragma unroll
-        for (int j = 0; j < SB; ++j) {
-          acc0 = f4_fma(vv[j], x0[j], acc0);
-          acc1 = f4_fma(vv[j], x1[j], acc1);
-        }
-      }
-      c = cn;
-      v = vn;
-      p += stride;
-    }
+    spmm_gather<D>(a, p, end, is_long ? 32 : LPR, gl, acc0, acc1);
     if (is_long) {  // combine the lane groups; group 0 owns the row
-#pragma unroll
-      for (int o = LPR; o < 32; o <<= 1) {
-        acc0.x += __shfl_xor_sync(SRB_FULL_MASK, acc0.x, o);
-        acc0.y += __shfl_xor_sync(SRB_FULL_MASK, acc0.y, o);
-        acc0.z += __shfl_xor_sync(SRB_FULL_MASK, acc0.z, o);
-        acc0.w += __shfl_xor_sync(SRB_FULL_MASK, acc0.w, o);
-        acc1.x += __shfl_xor_sync(SRB_FULL_MASK, acc1.x, o);
-        acc1.y += __shfl_xor_sync(SRB_FULL_MASK, acc1.y, o);
-        acc1.z += __shfl_xor_sync(SRB_FULL_MASK, acc1.z, o);
-        acc1.w += __shfl_xor_sync(SRB_FULL_MASK, acc1.w, o);
-      }
+      xor_reduce_groups(acc0, acc1, LPR);
       valid = valid && grp == 0;
     }
     spmm_epilogue<D>(a, row, gl, acc0, acc1, valid);
@@ -238,8 +281,9 @@ static int launch_spmm(const SpmmArgs& a, int d, cudaStream_t st) {
   if (a.n_rows == 0) return SRB_OK;
   const int threads = 256;
   const int rpw = 32 / (d / 8);
-  const long long items = (long long)a.n_long + ((long long)a.n_rows - a.n_long + rpw - 1) / rpw;
+  const long long items = (long long)a.n_long + ((long long)a.n_rows - a.n_vlong - a.n_long + rpw - 1) / rpw;
   long long blocks = (items + threads / 32 - 1) / (threads / 32);
+  if (blocks < a.n_vlong) blocks = a.n_vlong;
   const long long cap = (long long)sm_count() * 8;  // 8 x 256 threads = full residency
   if (blocks > cap) blocks = cap;
   switch (d) {
@@ -264,7 +308,8 @@ static int fill_args(const srb_spmm_desc* d, SpmmArgs& a) {
   a.vals = d->vals;
   a.row_order = d->row_order;
   a.n_rows = d->n_rows;
-  a.n_long = (d->row_order && d->n_long_rows > 0) ? (d->n_long_rows < d->n_rows ? d->n_long_rows : d->n_rows) : 0;
+  a.n_vlong = (d->row_order && d->n_vlong_rows > 0) ? (d->n_vlong_rows < d->n_rows ? d->n_vlong_rows : d->n_rows) : 0;
+  a.n_long = (d->row_order && d->n_long_rows > 0) ? (d->n_long_rows < d->n_rows - a.n_vlong ? d->n_long_rows : d->n_rows - a.n_vlong) : 0;
   a.X = d->X;
   a.Y = d->Y;
   a.extra = d->extra;
@@ -331,6 +376,8 @@ extern "C" int srb_encoder_forward(const srb_encoder_desc* e, void* stream) {
   SRB_REQUIRE(e->n_layers >= 0, "encoder: negative n_layers");
   SRB_REQUIRE(e->n_layers == 0 || (e->work0 && e->work1), "encoder: work buffers required");
   SRB_REQUIRE(e->include_ego || e->n_layers > 0, "encoder: mean over zero layers");
+  SRB_REQUIRE(!e->last_rows || (e->last_rows_out && e->last_rows_out != e->final_out && e->last_rows_out != e->E0),
+              "encoder: last_rows needs a separate last_rows_out buffer");
   const size_t nd = (size_t)e->n * e->d;
   cudaStream_t st = (cudaStream_t)stream;
   const int L = e->n_layers;
@@ -353,6 +400,7 @@ extern "C" int srb_encoder_forward(const srb_encoder_desc* e, void* stream) {
     s.vals = e->vals;
     s.row_order = e->row_order;
     s.n_long_rows = e->n_long_rows;
+    s.n_vlong_rows = e->n_vlong_rows;
     s.n_rows = e->n;
     s.n_cols = e->n;
     s.d = e->d;
@@ -372,6 +420,15 @@ extern "C" int srb_encoder_forward(const srb_encoder_desc* e, void* stream) {
     s.sum_in = (k == 0) ? (e->include_ego ? e->E0 : nullptr) : e->final_out;
     s.sum_out = e->final_out;
     s.sum_scale = last ? inv : 1.0f;
+    if (last && e->last_rows && e->n_last_rows > 0 && !(cl_hit && k == e->layer_cl - 1)) {
+      // only the listed rows of the final mean are consumed: one warp per listed row
+      s.row_order = e->last_rows;
+      s.n_rows = e->n_last_rows;
+      s.n_vlong_rows = e->n_last_rows;  // batch rows are degree-biased and unsorted: a CTA per listed row
+      s.n_long_rows = 0;
+      s.Y = nullptr;
+      s.sum_out = e->last_rows_out;  // out of place: duplicates in the list stay idempotent
+    }
     SRB_TRY(srb_spmm_csr(&s, stream));
     x = y;
   }

@@ -13,7 +13,8 @@ from . import _lib
 from ._lib import SrbError
 
 _SUPPORTED_D = (32, 64, 128)
-LONG_ROW_NNZ = 128  # rows at least this long are processed by a whole warp (srb_spmm_desc.n_long_rows)
+LONG_ROW_NNZ = 64    # rows at least this long are processed by a whole warp (srb_spmm_desc.n_long_rows)
+VLONG_ROW_NNZ = 256  # rows at least this long are processed by a whole CTA (srb_spmm_desc.n_vlong_rows)
 
 
 def _stream():
@@ -65,6 +66,7 @@ class SparseAdj:
         self.device = torch.device("cpu")
         self.rowptr = self.colidx = self.vals = self.row_order = None
         self.n_long = 0
+        self.n_vlong = 0
         self._t = None  # transposed handle (backward), built lazily
         self._symmetric = None
 
@@ -81,7 +83,8 @@ class SparseAdj:
         # long rows first: evens out the tail of the warp-per-row kernel on power-law graphs
         deg = np.diff(csr.indptr)
         self.row_order = torch.from_numpy(np.argsort(-deg, kind="stable").astype(np.int32)).to(dev)
-        self.n_long = int((deg >= LONG_ROW_NNZ).sum())  # rows that get a whole warp in the SpMM
+        self.n_vlong = int((deg >= VLONG_ROW_NNZ).sum())                # rows that get a whole CTA in the SpMM
+        self.n_long = int((deg >= LONG_ROW_NNZ).sum()) - self.n_vlong  # rows that get a whole warp
         self.device = dev
         return self
 
@@ -130,6 +133,7 @@ class SparseAdj:
         g = _lib.GraphCsr()
         g.rowptr, g.colidx, g.vals, g.row_order = _p(self.rowptr), _p(self.colidx), _p(self.vals), _p(self.row_order)
         g.n_long_rows = self.n_long
+        g.n_vlong_rows = self.n_vlong
         return g
 
 
@@ -146,7 +150,7 @@ def _spmm_raw(adj, x, y=None, **epi):
     desc = _lib.SpmmDesc()
     desc.rowptr, desc.colidx, desc.vals = _p(adj.rowptr), _p(adj.colidx), _p(adj.vals)
     desc.row_order = _p(adj.row_order)
-    desc.n_long_rows = adj.n_long
+    desc.n_long_rows, desc.n_vlong_rows = adj.n_long, adj.n_vlong
     desc.n_rows, desc.n_cols, desc.d = n_rows, n_cols, d
     desc.X = _p(x)
     desc.Y = _p(y)
@@ -204,7 +208,7 @@ def encoder_forward(adj, e0, n_layers, include_ego, noise=None, eps=0.0, layer_c
     w1 = torch.empty_like(e0)
     desc = _lib.EncoderDesc()
     desc.rowptr, desc.colidx, desc.vals, desc.row_order = _p(adj.rowptr), _p(adj.colidx), _p(adj.vals), _p(adj.row_order)
-    desc.n_long_rows = adj.n_long
+    desc.n_long_rows, desc.n_vlong_rows = adj.n_long, adj.n_vlong
     desc.n, desc.d, desc.n_layers, desc.include_ego, desc.layer_cl = n, d, n_layers, int(include_ego), int(layer_cl)
     if noise is not None:
         noise = _f32c(noise, "encoder noise")

@@ -30,7 +30,7 @@ def partition_rows(rowptr, world):
 class LocalShard:
     """The CSR slice A[R_r, :] of one rank (row pointers rebased, column ids global)."""
 
-    def __init__(self, csr, rank, world, long_row_nnz=128):
+    def __init__(self, csr, rank, world, long_row_nnz=64, vlong_row_nnz=256):
         csr = sp.csr_matrix(csr, dtype=np.float32)
         csr.sort_indices()
         self.n = csr.shape[0]
@@ -43,7 +43,8 @@ class LocalShard:
         self.vals = csr.data[lo:hi].astype(np.float32)
         deg = np.diff(self.rowptr)
         self.row_order = np.argsort(-deg, kind="stable").astype(np.int32)
-        self.n_long = int((deg >= long_row_nnz).sum())
+        self.n_vlong = int((deg >= vlong_row_nnz).sum())
+        self.n_long = int((deg >= long_row_nnz).sum()) - self.n_vlong
 
     @property
     def n_rows(self):
@@ -103,7 +104,7 @@ class ShardedPropagator:
         sd = _lib.SpmmShardedDesc()
         loc = sd.local
         loc.rowptr, loc.colidx, loc.vals = ops._p(self.rowptr), ops._p(self.colidx), ops._p(self.vals)
-        loc.row_order, loc.n_long_rows = ops._p(self.row_order), self.shard.n_long
+        loc.row_order, loc.n_long_rows, loc.n_vlong_rows = ops._p(self.row_order), self.shard.n_long, self.shard.n_vlong
         loc.n_rows, loc.n_cols, loc.d = self.shard.n_rows, self.N, self.d
         loc.X = ops._p(x)
         loc.extra_scale, loc.sum_scale = 1.0, 1.0
@@ -205,12 +206,14 @@ class ShardedXSimGCL:
         out = fin.clone()
         return out[: self.U], out[self.U:]
 
-    def step(self, words):
-        """One training step; `words` = batch buffer (srb_sampler_next_batch layout), same on all ranks."""
+    def step(self, words, words_dev=None):
+        """One training step; `words` = batch buffer (srb_sampler_next_batch layout), same on all ranks.
+        words_dev: the same buffer already resident on the device (then only the 3 header ints of the
+        host copy are read)."""
         torch, ops, p = self.torch, self.ops, self.prop
         lib = _lib.load()
         B, d, U, L = self.B, self.d, self.U, self.L
-        w = torch.as_tensor(np.asarray(words, dtype=np.int32)).to(p.dev)
+        w = words_dev if words_dev is not None else torch.as_tensor(np.asarray(words, dtype=np.int32)).to(p.dev)
         b, nu, ni = (int(x) for x in np.asarray(words[:3]))
         u_idx, i_idx, j_idx = w[4:4 + b], w[4 + B:4 + B + b], w[4 + 2 * B:4 + 2 * B + b]
         uq_u, uq_i = w[4 + 3 * B:4 + 3 * B + nu], w[4 + 4 * B:4 + 4 * B + ni]
