@@ -25,7 +25,7 @@ class SpmmDesc(C.Structure):
     _fields_ = [
         ("rowptr", VP), ("colidx", VP), ("vals", VP),
         ("n_rows", C.c_int32), ("n_cols", C.c_int32), ("d", C.c_int32),
-        ("row_order", VP), ("n_long_rows", C.c_int32), ("n_vlong_rows", C.c_int32), ("X", VP), ("Y", VP), ("extra", VP), ("extra_scale", C.c_float),
+        ("row_order", VP), ("n_long_rows", C.c_int32), ("n_vlong_rows", C.c_int32), ("n_vlong_dev", VP), ("col_mask", VP), ("X", VP), ("Y", VP), ("extra", VP), ("extra_scale", C.c_float),
         ("noise_mode", C.c_int32), ("noise", VP), ("eps", C.c_float),
         ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64), ("philox_step_dev", VP),
         ("sum_in", VP), ("sum_out", VP), ("sum_scale", C.c_float),
@@ -40,7 +40,7 @@ class EncoderDesc(C.Structure):
         ("n_vlong_rows", C.c_int32), ("n", C.c_int32), ("d", C.c_int32), ("n_layers", C.c_int32), ("include_ego", C.c_int32),
         ("layer_cl", C.c_int32), ("noise_mode", C.c_int32), ("noise", VP), ("eps", C.c_float),
         ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64), ("philox_step_dev", VP),
-        ("last_rows", VP), ("n_last_rows", C.c_int32), ("last_rows_out", VP),
+        ("last_rows", VP), ("n_last_rows", C.c_int32), ("last_rows_nv_dev", VP), ("last_rows_out", VP),
         ("E0", VP), ("final_out", VP), ("cl_out", VP), ("work0", VP), ("work1", VP),
     ]
 

@@ -34,7 +34,9 @@ struct Ws {
   float* nce_losses;   // [4]
   int32_t* idx_cat;    // [2B] SGL concatenated unique ids
   int32_t* n_cat;      // [1]
-  int32_t* batch_rows; // [3B] table rows of the batch (u, U+i, U+j), padded with the first entry
+  int32_t* batch_rows; // [3B] table rows of the batch (u, U+i, U+j), hubs first, padded with the first entry
+  int32_t* n_hub;      // [1] number of leading hub rows in batch_rows
+  uint32_t* row_mask;  // [(N+31)/32] bitmap of the batch's table rows (the rows the gradient seed touches)
   void* nce_ws;
   int64_t nce_ws_bytes;
 };
@@ -71,6 +73,8 @@ static int64_t carve(const srb_step_desc* s, Ws* w, char* base) {
   int32_t* i_cat = (int32_t*)take(2 * B * 4);
   int32_t* i_ncat = (int32_t*)take(4);
   int32_t* i_brows = (int32_t*)take(3 * B * 4);
+  int32_t* i_nhub = (int32_t*)take(4);
+  uint32_t* u_mask = (uint32_t*)take(graph ? ((N + 31) / 32) * 4 : 0);
   const int64_t nws = has_cl ? srb_infonce_workspace_bytes((int32_t)(2 * B), (int32_t)d, 2) : 0;
   void* v_nws = take(nws);
   if (w) {
@@ -92,6 +96,8 @@ static int64_t carve(const srb_step_desc* s, Ws* w, char* base) {
     w->idx_cat = i_cat;
     w->n_cat = i_ncat;
     w->batch_rows = i_brows;
+    w->n_hub = i_nhub;
+    w->row_mask = u_mask;
     w->nce_ws = v_nws;
     w->nce_ws_bytes = nws;
   }
@@ -108,15 +114,27 @@ __global__ void build_cat_idx_kernel(const int32_t* batch, int cap, int n_users,
   if (blockIdx.x == 0 && threadIdx.x == 0) *n_cat = nu + ni;
 }
 
-// rows of the [N, d] tables a batch touches: u, U + i, U + j (entries past the batch repeat row u[0])
-__global__ void build_batch_rows_kernel(const int32_t* batch, int cap, int n_users, int32_t* rows) {
+// rows of the [N, d] tables a batch touches: u, U + i, U + j (entries past the batch repeat row u[0]),
+// partitioned on the fly: rows with >= 256 non-zeros are packed at the front (they get a CTA each in
+// the SpMM), all others at the back (a warp each); *n_hub receives the split point.  One CTA.
+__global__ void __launch_bounds__(1024) build_batch_rows_kernel(const int32_t* batch, int cap, int n_users, const int32_t* rowptr,
+                                                                int32_t* rows, int32_t* n_hub, uint32_t* row_mask) {
+  __shared__ int front, back;
+  if (threadIdx.x == 0) front = 0, back = 0;
+  __syncthreads();
   const int b = min(batch[0], cap);
   const int32_t* u = batch + SRB_BATCH_HEADER;
   const int first = (b > 0) ? u[0] : 0;
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < 3 * cap; t += gridDim.x * blockDim.x) {
+  for (int t = threadIdx.x; t < 3 * cap; t += blockDim.x) {
     const int sec = t / cap, k = t % cap;
-    rows[t] = (k < b) ? (sec == 0 ? u[k] : n_users + u[sec * cap + k]) : first;
+    const int row = (k < b) ? (sec == 0 ? u[k] : n_users + u[sec * cap + k]) : first;
+    const bool hub = rowptr[row + 1] - rowptr[row] >= 256;
+    const int pos = hub ? atomicAdd(&front, 1) : 3 * cap - 1 - atomicAdd(&back, 1);
+    rows[pos] = row;
+    atomicOr(row_mask + (row >> 5), 1u << (row & 31));  // zeroed by the caller
   }
+  __syncthreads();
+  if (threadIdx.x == 0) *n_hub = front;
 }
 
 __global__ void finalize_losses_kernel(const float* bpr_losses, const float* nce_losses, int n_nce, float cl_rate, float* out) {
@@ -139,8 +157,9 @@ struct Chain {
 };
 
 static int spmm_simple(const srb_step_desc* s, const srb_graph_csr* g, const float* x, float* y, const float* extra,
-                       bool adam, cudaStream_t st) {
+                       bool adam, cudaStream_t st, const uint32_t* col_mask = nullptr) {
   srb_spmm_desc p = {};
+  p.col_mask = col_mask;
   p.rowptr = g->rowptr;
   p.colidx = g->colidx;
   p.vals = g->vals;
@@ -177,7 +196,7 @@ static int run_chain(const srb_step_desc* s, const Ws& w, const Chain& c, bool* 
   float* x = w.acc0;
   for (int k = L - 1; k >= 1; --k) {  // acc_k = A acc_{k+1} + (direct gradient of layer k)
     float* y = (x == w.acc0) ? w.acc1 : w.acc0;
-    SRB_TRY(spmm_simple(s, c.adj, x, y, nullptr, false, st));
+    SRB_TRY(spmm_simple(s, c.adj, x, y, nullptr, false, st, k == L - 1 ? w.row_mask : nullptr));  // seed: batch rows only
     SRB_TRY(scatter_segments(y, d, c.final_segs, st));
     if (c.layer_cl == k) SRB_TRY(scatter_segments(y, d, c.cl_segs, st));
     x = y;
@@ -192,8 +211,9 @@ static int run_chain(const srb_step_desc* s, const Ws& w, const Chain& c, bool* 
     SRB_TRY(scatter_segments(w.gd, d, c.ego_segs, st));
   }
   const float* extra = *gd_live ? w.gd : nullptr;
-  if (last) return spmm_simple(s, c.adj, x, nullptr, extra, true, st);
-  SRB_TRY(spmm_simple(s, c.adj, x, w.gd, extra, false, st));
+  const uint32_t* mask = (L == 1) ? w.row_mask : nullptr;
+  if (last) return spmm_simple(s, c.adj, x, nullptr, extra, true, st, mask);
+  SRB_TRY(spmm_simple(s, c.adj, x, w.gd, extra, false, st, mask));
   *gd_live = true;
   return SRB_OK;
 }
@@ -230,6 +250,7 @@ static int encoder(const srb_step_desc* s, const Ws& w, const srb_graph_csr* g, 
   } else {
     e.last_rows = w.batch_rows;
     e.n_last_rows = 3 * s->batch_cap;
+    e.last_rows_nv_dev = w.n_hub;
     e.last_rows_out = final_out;  // batch rows of the mean land here; the running sum lives in w.rsum
     e.final_out = w.rsum;
   }
@@ -283,7 +304,8 @@ extern "C" int srb_train_step(const srb_step_desc* s, void* stream) {
 
   // ---- forward ----
   if (s->model != SRB_MODEL_MF) {
-    build_batch_rows_kernel<<<(3 * B + 255) / 256, 256, 0, st>>>(s->batch, B, U, w.batch_rows);
+    SRB_TRY(check_cuda(cudaMemsetAsync(w.row_mask, 0, (size_t)((U + s->n_items + 31) / 32) * 4, st), "row mask memset"));
+    build_batch_rows_kernel<<<1, 1024, 0, st>>>(s->batch, B, U, s->adj.rowptr, w.batch_rows, w.n_hub, w.row_mask);
     SRB_TRY(post_launch("build_batch_rows_kernel"));
   }
   const float* table = s->params;  // table BPR gathers from

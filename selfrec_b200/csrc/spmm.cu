@@ -16,6 +16,8 @@ struct SpmmArgs {
   const float* vals;
   const int32_t* row_order;
   int32_t n_rows;
+  const int32_t* n_vlong_dev;  // optional device-side class split (see srb_spmm_desc)
+  const uint32_t* col_mask;    // optional: clear bit = X row is zero
   int32_t n_vlong; // leading entries of row_order that get a whole CTA
   int32_t n_long;  // following entries that get a whole warp
   const float* X;
@@ -165,6 +167,7 @@ __device__ __forceinline__ void spmm_gather(const SpmmArgs& a, int p, int end, i
   if (p + gl < end) {
     c = __ldg(a.colidx + p + gl);
     v = __ldg(a.vals + p + gl);
+    if (a.col_mask && !((__ldg(a.col_mask + (c >> 5)) >> (c & 31)) & 1u)) c = 0, v = 0.f;
   }
   while (__any_sync(SRB_FULL_MASK, p < end)) {
     int cn = 0;
@@ -172,6 +175,7 @@ __device__ __forceinline__ void spmm_gather(const SpmmArgs& a, int p, int end, i
     if (p + stride + gl < end) {  // prefetch the next iteration's pair
       cn = __ldg(a.colidx + p + stride + gl);
       vn = __ldg(a.vals + p + stride + gl);
+      if (a.col_mask && !((__ldg(a.col_mask + (cn >> 5)) >> (cn & 31)) & 1u)) cn = 0, vn = 0.f;
     }
 #pragma unroll
     for (int j0 = 0; j0 < LPR; j0 += SB) {
@@ -222,9 +226,14 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmArgs a) {
   const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
 
+  int n_vlong = a.n_vlong, n_long = a.n_long;
+  if (a.n_vlong_dev) {  // row list classified on the device: [very long | everything else, a warp each]
+    n_vlong = min(*a.n_vlong_dev, a.n_rows);
+    n_long = a.n_rows - n_vlong;
+  }
   // ---- class 1: one CTA per very long row ----
   __shared__ float4 part[8][2][LPR];
-  for (int vr = blockIdx.x; vr < a.n_vlong; vr += gridDim.x) {
+  for (int vr = blockIdx.x; vr < n_vlong; vr += gridDim.x) {
     const int row = a.row_order ? __ldg(a.row_order + vr) : vr;
     const int beg = __ldg(a.rowptr + row);
     const int end = __ldg(a.rowptr + row + 1);
@@ -253,8 +262,7 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmArgs a) {
   }
 
   // ---- classes 2 and 3: one warp per long row, one lane group per short row ----
-  const int base = a.n_vlong;
-  const int n_long = a.n_long;
+  const int base = n_vlong;
   const int n_items = n_long + (a.n_rows - base - n_long + RPW - 1) / RPW;
   for (int item = warp0; item < n_items; item += nwarps) {
     const bool is_long = item < n_long;  // warp-uniform
@@ -283,6 +291,7 @@ static int launch_spmm(const SpmmArgs& a, int d, cudaStream_t st) {
   const int rpw = 32 / (d / 8);
   const long long items = (long long)a.n_long + ((long long)a.n_rows - a.n_vlong - a.n_long + rpw - 1) / rpw;
   long long blocks = (items + threads / 32 - 1) / (threads / 32);
+  if (a.n_vlong_dev) blocks = ((long long)a.n_rows + threads / 32 - 1) / (threads / 32);  // worst case: a warp per row
   if (blocks < a.n_vlong) blocks = a.n_vlong;
   const long long cap = (long long)sm_count() * 8;  // 8 x 256 threads = full residency
   if (blocks > cap) blocks = cap;
@@ -309,6 +318,8 @@ static int fill_args(const srb_spmm_desc* d, SpmmArgs& a) {
   a.row_order = d->row_order;
   a.n_rows = d->n_rows;
   a.n_vlong = (d->row_order && d->n_vlong_rows > 0) ? (d->n_vlong_rows < d->n_rows ? d->n_vlong_rows : d->n_rows) : 0;
+  a.n_vlong_dev = d->row_order ? d->n_vlong_dev : nullptr;
+  a.col_mask = d->col_mask;
   a.n_long = (d->row_order && d->n_long_rows > 0) ? (d->n_long_rows < d->n_rows - a.n_vlong ? d->n_long_rows : d->n_rows - a.n_vlong) : 0;
   a.X = d->X;
   a.Y = d->Y;
@@ -424,8 +435,14 @@ extern "C" int srb_encoder_forward(const srb_encoder_desc* e, void* stream) {
       // only the listed rows of the final mean are consumed: one warp per listed row
       s.row_order = e->last_rows;
       s.n_rows = e->n_last_rows;
-      s.n_vlong_rows = e->n_last_rows;  // batch rows are degree-biased and unsorted: a CTA per listed row
-      s.n_long_rows = 0;
+      if (e->last_rows_nv_dev) {  // list classified on the device: [very long rows | the rest, a warp each]
+        s.n_vlong_rows = 0;
+        s.n_long_rows = 0;
+        s.n_vlong_dev = e->last_rows_nv_dev;
+      } else {
+        s.n_vlong_rows = e->n_last_rows;  // unsorted, degree-biased rows: a CTA per listed row
+        s.n_long_rows = 0;
+      }
       s.Y = nullptr;
       s.sum_out = e->last_rows_out;  // out of place: duplicates in the list stay idempotent
     }
