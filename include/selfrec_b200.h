@@ -62,8 +62,9 @@ typedef struct srb_spmm_desc {
   const int32_t* row_order;
   int32_t n_long_rows;
   int32_t n_vlong_rows;
-  /* optional device-side override: *n_vlong_dev very long rows lead row_order and ALL remaining
-   * entries get a warp each (row lists classified on the device, e.g. the rows of a batch) */
+  /* optional device-side classification (row lists built on the device, e.g. the rows of a batch):
+   * n_vlong_dev[0..2] = number of very long / long / short rows; row_order then holds three segments
+   * of capacity n_rows each: [0, n_rows) very long, [n_rows, 2 n_rows) long, [2 n_rows, 3 n_rows) short */
   const int32_t* n_vlong_dev;
   /* optional bitmap over columns (bit c of word c/32): a clear bit promises X[c,:] == 0, so the
      non-zero is skipped without touching X (row-sparse X: the first backward product). */
@@ -122,7 +123,7 @@ typedef struct srb_encoder_desc {
    * the batch rows of a training step -- nothing else reads the final mean there */
   const int32_t* last_rows;
   int32_t n_last_rows;
-  const int32_t* last_rows_nv_dev; /* device: how many leading entries of last_rows are very long rows */
+  const int32_t* last_rows_nv_dev; /* device-classified list: class sizes [3]; last_rows = 3 segments of n_last_rows (see srb_spmm_desc.n_vlong_dev) */
   float* last_rows_out; /* [n, d], required with last_rows: receives the final mean of the listed rows
                            (final_out then only holds the running sum; the list may contain duplicates,
                            so the last layer must not update the running sum in place) */

@@ -34,8 +34,8 @@ struct Ws {
   float* nce_losses;   // [4]
   int32_t* idx_cat;    // [2B] SGL concatenated unique ids
   int32_t* n_cat;      // [1]
-  int32_t* batch_rows; // [3B] table rows of the batch (u, U+i, U+j), hubs first, padded with the first entry
-  int32_t* n_hub;      // [1] number of leading hub rows in batch_rows
+  int32_t* batch_rows; // [3][3B] table rows of the batch (u, U+i, U+j) by degree class: >= 256, >= 64, shorter
+  int32_t* n_hub;      // [3] rows per class
   uint32_t* row_mask;  // [(N+31)/32] bitmap of the batch's table rows (the rows the gradient seed touches)
   void* nce_ws;
   int64_t nce_ws_bytes;
@@ -72,9 +72,10 @@ static int64_t carve(const srb_step_desc* s, Ws* w, char* base) {
   float* f_nl = (float*)take(4 * 4);
   int32_t* i_cat = (int32_t*)take(2 * B * 4);
   int32_t* i_ncat = (int32_t*)take(4);
-  int32_t* i_brows = (int32_t*)take(3 * B * 4);
-  int32_t* i_nhub = (int32_t*)take(4);
-  uint32_t* u_mask = (uint32_t*)take(graph ? ((N + 31) / 32) * 4 : 0);
+  int32_t* i_brows = (int32_t*)take(3 * 3 * B * 4);
+  // [n_hub, back counter, pad, pad | row bitmap]: one memset clears all of it
+  int32_t* i_nhub = (int32_t*)take(graph ? 16 + ((N + 31) / 32) * 4 : 16);
+  uint32_t* u_mask = (uint32_t*)(i_nhub + 4);
   const int64_t nws = has_cl ? srb_infonce_workspace_bytes((int32_t)(2 * B), (int32_t)d, 2) : 0;
   void* v_nws = take(nws);
   if (w) {
@@ -114,27 +115,29 @@ __global__ void build_cat_idx_kernel(const int32_t* batch, int cap, int n_users,
   if (blockIdx.x == 0 && threadIdx.x == 0) *n_cat = nu + ni;
 }
 
-// rows of the [N, d] tables a batch touches: u, U + i, U + j (entries past the batch repeat row u[0]),
-// partitioned on the fly: rows with >= 256 non-zeros are packed at the front (they get a CTA each in
-// the SpMM), all others at the back (a warp each); *n_hub receives the split point.  One CTA.
-__global__ void __launch_bounds__(1024) build_batch_rows_kernel(const int32_t* batch, int cap, int n_users, const int32_t* rowptr,
-                                                                int32_t* rows, int32_t* n_hub, uint32_t* row_mask) {
-  __shared__ int front, back;
-  if (threadIdx.x == 0) front = 0, back = 0;
-  __syncthreads();
+// rows of the [N, d] tables a batch touches: u, U + i, U + j, classified by degree on the fly for the
+// last-layer SpMM (>= 256 non-zeros: a CTA each, >= 64: a warp each, shorter: a lane group each) into
+// three segments of capacity 3*cap; counters[c] ends up as the size of class c.  Also sets the rows'
+// bits in row_mask.  counters[0..3] and row_mask are zeroed by the caller.
+__global__ void __launch_bounds__(256) build_batch_rows_kernel(const int32_t* batch, int cap, int n_users, const int32_t* rowptr,
+                                                               int32_t* rows, int32_t* counters, uint32_t* row_mask) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = min(batch[0], cap);
+  const int sec = t / cap, k = t % cap;
+  if (sec >= 3 || k >= b) return;
   const int32_t* u = batch + SRB_BATCH_HEADER;
-  const int first = (b > 0) ? u[0] : 0;
-  for (int t = threadIdx.x; t < 3 * cap; t += blockDim.x) {
-    const int sec = t / cap, k = t % cap;
-    const int row = (k < b) ? (sec == 0 ? u[k] : n_users + u[sec * cap + k]) : first;
-    const bool hub = rowptr[row + 1] - rowptr[row] >= 256;
-    const int pos = hub ? atomicAdd(&front, 1) : 3 * cap - 1 - atomicAdd(&back, 1);
-    rows[pos] = row;
-    atomicOr(row_mask + (row >> 5), 1u << (row & 31));  // zeroed by the caller
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) *n_hub = front;
+  const int row = (sec == 0) ? u[k] : n_users + u[sec * cap + k];
+  const int deg = rowptr[row + 1] - rowptr[row];
+  const int cls = deg >= 256 ? 0 : (deg >= 64 ? 1 : 2);
+  // warp-aggregated slot allocation per class
+  const unsigned mine = __match_any_sync(__activemask(), cls);
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(mine) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(counters + cls, __popc(mine));
+  base = __shfl_sync(mine, base, leader);
+  rows[cls * 3 * cap + base + __popc(mine & ((1u << lane) - 1))] = row;
+  atomicOr(row_mask + (row >> 5), 1u << (row & 31));
 }
 
 __global__ void finalize_losses_kernel(const float* bpr_losses, const float* nce_losses, int n_nce, float cl_rate, float* out) {
@@ -304,8 +307,8 @@ extern "C" int srb_train_step(const srb_step_desc* s, void* stream) {
 
   // ---- forward ----
   if (s->model != SRB_MODEL_MF) {
-    SRB_TRY(check_cuda(cudaMemsetAsync(w.row_mask, 0, (size_t)((U + s->n_items + 31) / 32) * 4, st), "row mask memset"));
-    build_batch_rows_kernel<<<1, 1024, 0, st>>>(s->batch, B, U, s->adj.rowptr, w.batch_rows, w.n_hub, w.row_mask);
+    SRB_TRY(check_cuda(cudaMemsetAsync(w.n_hub, 0, 16 + (size_t)((U + s->n_items + 31) / 32) * 4, st), "row mask memset"));
+    build_batch_rows_kernel<<<(3 * B + 255) / 256, 256, 0, st>>>(s->batch, B, U, s->adj.rowptr, w.batch_rows, w.n_hub, w.row_mask);
     SRB_TRY(post_launch("build_batch_rows_kernel"));
   }
   const float* table = s->params;  // table BPR gathers from

@@ -59,6 +59,12 @@ struct NceArgs {
   NceProblem p[4];
 };
 
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
 __device__ __forceinline__ int nce_n(const NceProblem& p) { return p.n_dev ? min(*p.n_dev, p.n) : p.n; }
 
 template <int D>
@@ -123,6 +129,72 @@ __global__ void __launch_bounds__(256) nce_prep_kernel(const NceArgs a) {
     p.inv1[i] = i1;
     p.inv2[i] = i2;
     p.diag[i] = s12 * a.inv_tau;
+  }
+}
+
+// Tensor-core pipeline (d = 64): gather + normalise 32 rows per CTA; besides the exact rows it writes the
+// TF32 hi / lo parts (x = hi + lo, hi = rna_tf32(x); the tensor core truncates lo) of both views, row-major
+// and transposed (through shared memory, so the transposed stores are 128-byte coalesced), behind dV2:
+//   hi: [V1 | V2 | V1^T | V2^T]   then lo: the same four
+__global__ void __launch_bounds__(256) nce_prep_tc_kernel(const NceArgs a) {
+  constexpr int D = 64;
+  __shared__ float t1[32][D + 1], t2[32][D + 1];
+  const NceProblem& p = a.p[blockIdx.y];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i0 = blockIdx.x * 32;
+  const int n = nce_n(p);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *p.loss_acc = 0.f;
+  const size_t nd = (size_t)a.np * D;
+  float* hi = p.dV2 + nd;
+  float* lo = hi + 4 * nd;
+#pragma unroll 1
+  for (int rr = 0; rr < 4; ++rr) {
+    const int il = warp * 4 + rr, i = i0 + il;
+    const int c = lane * 2;
+    float2 v1 = make_float2(0.f, 0.f), v2 = make_float2(0.f, 0.f);
+    if (i < n) {
+      const int r = p.idx[i];
+      v1 = *reinterpret_cast<const float2*>(p.table1 + (size_t)(r + p.row_off1) * D + c);
+      v2 = *reinterpret_cast<const float2*>(p.table2 + (size_t)(r + p.row_off2) * D + c);
+      v1.x *= p.scale1, v1.y *= p.scale1, v2.x *= p.scale2, v2.y *= p.scale2;
+    }
+    const float s1 = warp_sum(v1.x * v1.x + v1.y * v1.y);
+    const float s2 = warp_sum(v2.x * v2.x + v2.y * v2.y);
+    float i1 = 1.f, i2 = 1.f;
+    if (a.b_cos) {  // F.normalize divides (x / max(norm, eps)); keep the division for rounding parity
+      const float n1 = fmaxf(sqrtf(s1), 1e-12f), n2 = fmaxf(sqrtf(s2), 1e-12f);
+      i1 = 1.f / n1, i2 = 1.f / n2;
+      v1.x /= n1, v1.y /= n1, v2.x /= n2, v2.y /= n2;
+    }
+    const float s12 = warp_sum(v1.x * v2.x + v1.y * v2.y);
+    const size_t o = (size_t)i * D + c;
+    *reinterpret_cast<float2*>(p.V1 + o) = v1;
+    *reinterpret_cast<float2*>(p.V2 + o) = v2;
+    *reinterpret_cast<float2*>(p.dV1 + o) = make_float2(0.f, 0.f);
+    *reinterpret_cast<float2*>(p.dV2 + o) = make_float2(0.f, 0.f);
+    const float2 h1 = make_float2(tf32_rna(v1.x), tf32_rna(v1.y)), h2 = make_float2(tf32_rna(v2.x), tf32_rna(v2.y));
+    *reinterpret_cast<float2*>(hi + o) = h1;
+    *reinterpret_cast<float2*>(hi + nd + o) = h2;
+    *reinterpret_cast<float2*>(lo + o) = make_float2(v1.x - h1.x, v1.y - h1.y);
+    *reinterpret_cast<float2*>(lo + nd + o) = make_float2(v2.x - h2.x, v2.y - h2.y);
+    t1[il][c] = v1.x, t1[il][c + 1] = v1.y;
+    t2[il][c] = v2.x, t2[il][c + 1] = v2.y;
+    if (lane == 0) {
+      p.inv1[i] = i1;
+      p.inv2[i] = i2;
+      p.diag[i] = s12 * a.inv_tau;
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < D * 32; e += 256) {
+    const int dc = e >> 5, il = e & 31;
+    const size_t o = (size_t)dc * a.np + i0 + il;
+    const float x1 = t1[il][dc], x2 = t2[il][dc];
+    const float g1 = tf32_rna(x1), g2 = tf32_rna(x2);
+    hi[2 * nd + o] = g1;
+    hi[3 * nd + o] = g2;
+    lo[2 * nd + o] = x1 - g1;
+    lo[3 * nd + o] = x2 - g2;
   }
 }
 
@@ -453,25 +525,14 @@ static int nce_impl() {
   return impl;
 }
 
-// x = hi + lo with hi = rna_tf32(x), lo = rna_tf32(x - hi)   ("3xTF32" operand split)
-__global__ void __launch_bounds__(256) nce_split_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo,
-                                                       long long n4) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    const float4 v = reinterpret_cast<const float4*>(src)[i];
-    const float4 h = make_float4(to_tf32_rna(v.x), to_tf32_rna(v.y), to_tf32_rna(v.z), to_tf32_rna(v.w));
-    reinterpret_cast<float4*>(hi)[i] = h;
-    reinterpret_cast<float4*>(lo)[i] = make_float4(to_tf32_rna(v.x - h.x), to_tf32_rna(v.y - h.y), to_tf32_rna(v.z - h.z), to_tf32_rna(v.w - h.w));
-  }
-}
-
-// tensor-core pipeline: prep (exact) -> round copies -> LSE -> GRAD-A / GRAD-B -> finish
+// tensor-core pipeline: prep (exact rows + TF32 hi/lo parts) -> LSE -> GRAD-A -> GRAD-B -> finish
 static int nce_launch_tc(const NceArgs& a, int n_problems, cudaStream_t st) {
   const int np = a.np;
   const int d = NT_D;
   {
-    dim3 grid((np + 7) / 8, n_problems);
-    nce_prep_kernel<64><<<grid, 256, 0, st>>>(a);
-    SRB_TRY(post_launch("nce_prep_kernel"));
+    dim3 grid(np / 32, n_problems);
+    nce_prep_tc_kernel<<<grid, 256, 0, st>>>(a);
+    SRB_TRY(post_launch("nce_prep_tc_kernel"));
   }
   NtMaps maps;
   NtArgs t;
@@ -487,11 +548,9 @@ static int nce_launch_tc(const NceArgs& a, int n_problems, cudaStream_t st) {
   const long long nd = (long long)np * d;
   for (int q = 0; q < n_problems; ++q) {
     const NceProblem& p = a.p[q];
-    // hi / lo parts live behind dV2: hi of (V1 V2 V1T V2T) then lo of the same four
+    // hi / lo parts live behind dV2 (written by prep): hi of (V1 V2 V1T V2T) then lo of the same four
     float* hi = p.dV2 + nd;
     float* lo = hi + 4 * nd;
-    nce_split_kernel<<<128, 256, 0, st>>>(p.V1, hi, lo, 4 * nd / 4);  // V1 V2 V1T V2T are contiguous
-    SRB_TRY(post_launch("nce_split_kernel"));
     for (int h = 0; h < 2; ++h) {
       float* r = h ? lo : hi;
       SRB_REQUIRE(make_tmap_f32_rows(&maps.v1r[q][h], r, (uint64_t)np, d, NT_T) == 0 &&
@@ -653,8 +712,9 @@ extern "C" int srb_infonce_fwd_bwd(const srb_infonce_desc* d, void* stream) {
   }
   cudaStream_t st = (cudaStream_t)stream;
   const int impl = srb::nce_impl();
-  if (d->d == 64 && d->b_cos && impl != 1 && d->n_problems <= 2) return srb::nce_launch_tc(a, d->n_problems, st);
-  SRB_REQUIRE(impl != 2, "infonce: SRB_NCE_IMPL=2 (tensor cores) needs d == 64 and b_cos");
+  // the tensor-core LSE pass shifts by the bound 1/tau of a cosine logit: needs exp(-2/tau) representable
+  if (d->d == 64 && d->b_cos && impl != 1 && d->n_problems <= 2 && a.inv_tau <= 40.f) return srb::nce_launch_tc(a, d->n_problems, st);
+  SRB_REQUIRE(impl != 2, "infonce: SRB_NCE_IMPL=2 (tensor cores) needs d == 64, b_cos and temperature >= 0.025");
   switch (d->d) {
     case 32: return srb::nce_launch<32>(a, d->n_problems, st);
     case 64: return srb::nce_launch<64>(a, d->n_problems, st);

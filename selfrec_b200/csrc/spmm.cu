@@ -226,15 +226,22 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmArgs a) {
   const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
 
-  int n_vlong = a.n_vlong, n_long = a.n_long;
-  if (a.n_vlong_dev) {  // row list classified on the device: [very long | everything else, a warp each]
-    n_vlong = min(*a.n_vlong_dev, a.n_rows);
-    n_long = a.n_rows - n_vlong;
+  int n_vlong = a.n_vlong, n_long = a.n_long, n_short = a.n_rows - a.n_vlong - a.n_long;
+  const int32_t* ro_v = a.row_order;  // the three classes' row lists (null: identity order)
+  const int32_t* ro_l = a.row_order ? a.row_order + n_vlong : nullptr;
+  const int32_t* ro_s = a.row_order ? ro_l + n_long : nullptr;
+  int id_l = n_vlong, id_s = n_vlong + n_long;
+  if (a.n_vlong_dev) {  // row list classified on the device: three segments of capacity n_rows
+    n_vlong = min(a.n_vlong_dev[0], a.n_rows);
+    n_long = min(a.n_vlong_dev[1], a.n_rows);
+    n_short = min(a.n_vlong_dev[2], a.n_rows);
+    ro_l = a.row_order + a.n_rows;
+    ro_s = a.row_order + 2 * a.n_rows;
   }
   // ---- class 1: one CTA per very long row ----
   __shared__ float4 part[8][2][LPR];
   for (int vr = blockIdx.x; vr < n_vlong; vr += gridDim.x) {
-    const int row = a.row_order ? __ldg(a.row_order + vr) : vr;
+    const int row = ro_v ? __ldg(ro_v + vr) : vr;
     const int beg = __ldg(a.rowptr + row);
     const int end = __ldg(a.rowptr + row + 1);
     const int per = ((end - beg + 255) / 256) * 32;  // non-zeros per warp, a multiple of 32
@@ -262,15 +269,15 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmArgs a) {
   }
 
   // ---- classes 2 and 3: one warp per long row, one lane group per short row ----
-  const int base = n_vlong;
-  const int n_items = n_long + (a.n_rows - base - n_long + RPW - 1) / RPW;
+  const int n_items = n_long + (n_short + RPW - 1) / RPW;
   for (int item = warp0; item < n_items; item += nwarps) {
     const bool is_long = item < n_long;  // warp-uniform
-    const int ridx = base + (is_long ? item : n_long + (item - n_long) * RPW + grp);
-    bool valid = ridx < a.n_rows;
+    const int k = is_long ? item : (item - n_long) * RPW + grp;  // index within the class
+    bool valid = is_long || k < n_short;
     int row = 0, p = 0, end = 0;
     if (valid) {
-      row = a.row_order ? __ldg(a.row_order + ridx) : ridx;
+      if (is_long) row = ro_l ? __ldg(ro_l + k) : id_l + k;
+      else row = ro_s ? __ldg(ro_s + k) : id_s + k;
       p = __ldg(a.rowptr + row);
       end = __ldg(a.rowptr + row + 1);
     }
@@ -291,7 +298,7 @@ static int launch_spmm(const SpmmArgs& a, int d, cudaStream_t st) {
   const int rpw = 32 / (d / 8);
   const long long items = (long long)a.n_long + ((long long)a.n_rows - a.n_vlong - a.n_long + rpw - 1) / rpw;
   long long blocks = (items + threads / 32 - 1) / (threads / 32);
-  if (a.n_vlong_dev) blocks = ((long long)a.n_rows + threads / 32 - 1) / (threads / 32);  // worst case: a warp per row
+  if (a.n_vlong_dev) blocks = ((long long)a.n_rows + threads / 32 - 1) / (threads / 32);  // worst case: every row long, a warp each
   if (blocks < a.n_vlong) blocks = a.n_vlong;
   const long long cap = (long long)sm_count() * 8;  // 8 x 256 threads = full residency
   if (blocks > cap) blocks = cap;
@@ -435,7 +442,7 @@ extern "C" int srb_encoder_forward(const srb_encoder_desc* e, void* stream) {
       // only the listed rows of the final mean are consumed: one warp per listed row
       s.row_order = e->last_rows;
       s.n_rows = e->n_last_rows;
-      if (e->last_rows_nv_dev) {  // list classified on the device: [very long rows | the rest, a warp each]
+      if (e->last_rows_nv_dev) {  // list classified on the device: three segments of n_last_rows entries
         s.n_vlong_rows = 0;
         s.n_long_rows = 0;
         s.n_vlong_dev = e->last_rows_nv_dev;

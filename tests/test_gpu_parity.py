@@ -175,7 +175,8 @@ def test_bpr_l2_infonce_ops_match_reference(torch_cuda, golden):
         loss = InfoNCE(v1, v2, float(lo[f"nce_{tag}_tau"]), bool(lo[f"nce_{tag}_cos"]))
         g1, g2 = torch.autograd.grad(loss, (v1, v2))
         ref = float(lo[f"nce_{tag}_loss"])
-        assert abs(loss.item() - ref) <= RTOL * max(abs(ref), 1e-3), tag
+        # the loss is a mean of (lse - S_ii) with |S| up to 1/tau: fp32 resolution of the terms bounds the abs error
+        assert abs(loss.item() - ref) <= RTOL * max(abs(ref), 1e-3) + 2e-7 / float(lo[f"nce_{tag}_tau"]), tag
         scale = max(np.abs(lo[f"nce_{tag}_g1"]).max(), 1e-12)
         # absolute floor: fp32 resolution of a logit (eps32 / tau) through 1/(n tau), a unit-vector entry and 1/||v||
         # (the n = 1 case has an exactly-zero reference gradient, where only an absolute bound is meaningful)
