@@ -11,8 +11,9 @@ A step  = one pass of the hot path over one batch: propagate (3 SpMM) -> gather 
           InfoNCE -> Horner backward (3 SpMM) -> Adam, on in-kernel Philox noise.
 value   = steps/s with the batch indices already resident in HBM (a device pool of pre-sampled
           batches), CUDA-graph replay, CUDA-event timing, max over ranks.
-e2e     = the same metric through the public API with HOST buffers: native sampler ->
-          TrainEngine.step(words) (pinned H2D copy) -> loss read back (D2H) every step.
+e2e     = the same metric through the public API with HOST buffers, every step: native sampler ->
+          TrainEngine.step(words, fetch_loss=True) (pinned H2D copy of the batch, the step, D2H copy of
+          the losses); the host reads the loss of step t while step t+1 runs (the last one after the loop).
 --impl reference times the reference's CPU PyTorch path (oracle/torch_port.py, the op-for-op
 port pinned against the reference) on the host cores; rank 0 only.
 """
@@ -252,16 +253,21 @@ def run_ours(args, rank, world, local_rank):
     del flush
 
     # ---- e2e: public API, host buffers, H2D + D2H every step -------------------------------
+    # (the engine's public step(): pinned H2D of the sampled batch, the step graph, D2H of the loss values into
+    # pinned memory; the loss of step t is read on the host while step t+1 runs, the last one after the loop)
     gen = eng.batches()
     for _ in range(max(args.warmup, 3)):
-        eng.step(next(gen))
-        eng.losses.cpu()
+        eng.step(next(gen), fetch_loss=True).get()
     torch.cuda.synchronize()
     barrier()
     t0 = time.perf_counter()
+    pending = None
     for _ in range(args.steps):
-        eng.step(next(gen))
-        loss_host = eng.losses.cpu()  # D2H read of the step's result (syncs)
+        h = eng.step(next(gen), fetch_loss=True)
+        if pending is not None:
+            loss_host = pending.get()  # D2H read of the previous step's result
+        pending = h
+    loss_host = pending.get()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)

@@ -233,6 +233,19 @@ int srb_scatter_add_rows(float* dst, int32_t d, const float* src, const int32_t*
                          int32_t n, const int32_t* n_dev, int32_t row_off, float scale,
                          void* stream);
 
+/* Up to 8 such scatters into the same table in ONE launch (the gradient of several gathers of
+ * one tensor).  n_dev (optional, device) overrides n with min(*n_dev, n). */
+typedef struct srb_scatter_seg {
+  const float* src;     /* [n, d] compact rows */
+  const int32_t* rows;  /* [n] destination rows */
+  const int32_t* n_dev;
+  int32_t n;
+  int32_t row_off;
+  float scale;
+} srb_scatter_seg;
+int srb_scatter_add_segments(float* dst, int32_t d, int32_t n_segs, const srb_scatter_seg* segs,
+                             void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Adam (R10): torch.optim.Adam defaults, dense (MF.py:15 ... XSimGCL.py:25).
  * srb_adam_prepare: one tiny launch; increments the device step counter and writes

@@ -45,6 +45,10 @@ class EncoderDesc(C.Structure):
     ]
 
 
+class ScatterSeg(C.Structure):
+    _fields_ = [("src", VP), ("rows", VP), ("n_dev", VP), ("n", C.c_int32), ("row_off", C.c_int32), ("scale", C.c_float)]
+
+
 class BprDesc(C.Structure):
     _fields_ = [
         ("emb", VP), ("l2_emb", VP), ("n_users", C.c_int32), ("d", C.c_int32),
@@ -117,6 +121,7 @@ SYMBOLS = {
     "srb_l2_reg_fwd": (C.c_int, [C.c_int32, C.POINTER(VP), c_i64p, c_i32p, C.c_float, VP, VP, VP]),
     "srb_l2_reg_bwd": (C.c_int, [C.c_int32, C.POINTER(VP), C.POINTER(VP), c_i64p, c_i32p, C.c_float, VP, VP, VP]),
     "srb_scatter_add_rows": (C.c_int, [VP, C.c_int32, VP, VP, C.c_int32, VP, C.c_int32, C.c_float, VP]),
+    "srb_scatter_add_segments": (C.c_int, [VP, C.c_int32, C.c_int32, VP, VP]),
     "srb_adam_prepare": (C.c_int, [VP, VP, C.c_double, C.c_double, C.c_double, VP]),
     "srb_adam_step": (C.c_int, [VP, VP, VP, VP, C.c_int64, VP, C.c_double, C.c_double, C.c_float, VP]),
     "srb_topk_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),

@@ -336,6 +336,18 @@ extern "C" int srb_scatter_add_rows(float* dst, int32_t d, const float* src, con
   return srb::scatter_segments(dst, d, segs, (cudaStream_t)stream);
 }
 
+extern "C" int srb_scatter_add_segments(float* dst, int32_t d, int32_t n_segs, const srb_scatter_seg* in, void* stream) {
+  SRB_REQUIRE(dst && in, "scatter: null pointer");
+  SRB_REQUIRE(n_segs >= 0 && n_segs <= 8, "scatter: 0..8 segments per launch");
+  srb::ScatterSegs segs;
+  segs.count = n_segs;
+  for (int q = 0; q < n_segs; ++q) {
+    SRB_REQUIRE(in[q].src && in[q].rows && in[q].n >= 0, "scatter: bad segment %d", q);
+    segs.s[q] = {in[q].src, in[q].rows, in[q].n_dev, in[q].n, in[q].row_off, in[q].scale};
+  }
+  return srb::scatter_segments(dst, d, segs, (cudaStream_t)stream);
+}
+
 extern "C" int srb_adam_prepare(int32_t* step_dev, float* scalars_dev, double lr, double beta1, double beta2, void* stream) {
   SRB_REQUIRE(step_dev && scalars_dev, "adam_prepare: null pointer");
   srb::adam_prepare_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev, scalars_dev, lr, beta1, beta2);

@@ -116,7 +116,7 @@ __global__ void build_cat_idx_kernel(const int32_t* batch, int cap, int n_users,
 }
 
 // rows of the [N, d] tables a batch touches: u, U + i, U + j, classified by degree on the fly for the
-// last-layer SpMM (>= 256 non-zeros: a CTA each, >= 64: a warp each, shorter: a lane group each) into
+// last-layer SpMM (a CTA per long row, a warp per other row; the lane-group class stays empty) into
 // three segments of capacity 3*cap; counters[c] ends up as the size of class c.  Also sets the rows'
 // bits in row_mask.  counters[0..3] and row_mask are zeroed by the caller.
 __global__ void __launch_bounds__(256) build_batch_rows_kernel(const int32_t* batch, int cap, int n_users, const int32_t* rowptr,
@@ -128,7 +128,8 @@ __global__ void __launch_bounds__(256) build_batch_rows_kernel(const int32_t* ba
   const int32_t* u = batch + SRB_BATCH_HEADER;
   const int row = (sec == 0) ? u[k] : n_users + u[sec * cap + k];
   const int deg = rowptr[row + 1] - rowptr[row];
-  const int cls = deg >= 256 ? 0 : (deg >= 64 ? 1 : 2);
+  // only ~3B rows: parallelism is scarce, so no row shares a warp and rows above 4 warp-iterations get a CTA
+  const int cls = deg >= 128 ? 0 : 1;
   // warp-aggregated slot allocation per class
   const unsigned mine = __match_any_sync(__activemask(), cls);
   const int lane = threadIdx.x & 31;
@@ -189,19 +190,46 @@ static int spmm_simple(const srb_step_desc* s, const srb_graph_csr* g, const flo
 
 // Horner backward of one encoder.  `gd` accumulates the E0 gradient across chains; the last
 // chain applies Adam.  gd_live says whether gd already holds earlier chains' contributions.
+// BPR + L2 and InfoNCE only read the encoder outputs and write disjoint buffers: the step forks BPR onto a
+// side stream (event dependencies, so a stream capture records the fork and join) and joins before the
+// losses are combined.  One side stream + two events per device, created on first use.
+struct ForkRes {
+  cudaStream_t side;
+  cudaEvent_t fork, join;
+  bool ok;
+};
+static ForkRes* fork_res() {
+  static ForkRes res[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  ForkRes& r = res[dev];
+  if (!r.ok) {
+    if (cudaStreamCreateWithFlags(&r.side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&r.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&r.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    r.ok = true;
+  }
+  return &r;
+}
+
+static ScatterSegs merged(const ScatterSegs& a, const ScatterSegs* b) {  // one launch instead of two
+  ScatterSegs m = a;
+  if (b)
+    for (int q = 0; q < b->count && m.count < 8; ++q) m.s[m.count++] = b->s[q];
+  return m;
+}
+
 static int run_chain(const srb_step_desc* s, const Ws& w, const Chain& c, bool* gd_live, bool last, cudaStream_t st) {
   const int L = s->n_layers, d = s->d;
   const size_t bytes = (size_t)(s->n_users + s->n_items) * d * 4;
   // seed: gradient w.r.t. the output of layer L
   SRB_TRY(check_cuda(cudaMemsetAsync(w.acc0, 0, bytes, st), "chain memset"));
-  SRB_TRY(scatter_segments(w.acc0, d, c.final_segs, st));
-  if (c.layer_cl == L) SRB_TRY(scatter_segments(w.acc0, d, c.cl_segs, st));
+  SRB_TRY(scatter_segments(w.acc0, d, merged(c.final_segs, c.layer_cl == L ? &c.cl_segs : nullptr), st));
   float* x = w.acc0;
   for (int k = L - 1; k >= 1; --k) {  // acc_k = A acc_{k+1} + (direct gradient of layer k)
     float* y = (x == w.acc0) ? w.acc1 : w.acc0;
     SRB_TRY(spmm_simple(s, c.adj, x, y, nullptr, false, st, k == L - 1 ? w.row_mask : nullptr));  // seed: batch rows only
-    SRB_TRY(scatter_segments(y, d, c.final_segs, st));
-    if (c.layer_cl == k) SRB_TRY(scatter_segments(y, d, c.cl_segs, st));
+    SRB_TRY(scatter_segments(y, d, merged(c.final_segs, c.layer_cl == k ? &c.cl_segs : nullptr), st));
     x = y;
   }
   const bool ego_add = (c.include_ego && c.final_segs.count) || c.ego_segs.count;
@@ -210,8 +238,8 @@ static int run_chain(const srb_step_desc* s, const Ws& w, const Chain& c, bool* 
     *gd_live = true;
   }
   if (ego_add) {
-    if (c.include_ego) SRB_TRY(scatter_segments(w.gd, d, c.final_segs, st));
-    SRB_TRY(scatter_segments(w.gd, d, c.ego_segs, st));
+    if (c.include_ego) SRB_TRY(scatter_segments(w.gd, d, merged(c.final_segs, &c.ego_segs), st));
+    else SRB_TRY(scatter_segments(w.gd, d, c.ego_segs, st));
   }
   const float* extra = *gd_live ? w.gd : nullptr;
   const uint32_t* mask = (L == 1) ? w.row_mask : nullptr;
@@ -342,7 +370,12 @@ extern "C" int srb_train_step(const srb_step_desc* s, void* stream) {
       break;
   }
 
-  // ---- BPR + L2 ----
+  // ---- BPR + L2 (on the side stream when an InfoNCE follows) ----
+  ForkRes* fk = (s->model == SRB_MODEL_XSIMGCL || s->model == SRB_MODEL_SIMGCL || s->model == SRB_MODEL_SGL) ? fork_res() : nullptr;
+  if (fk) {
+    SRB_TRY(check_cuda(cudaEventRecord(fk->fork, st), "fork record"));
+    SRB_TRY(check_cuda(cudaStreamWaitEvent(fk->side, fk->fork, 0), "fork wait"));
+  }
   {
     srb_bpr_desc p = {};
     p.emb = table;
@@ -364,7 +397,8 @@ extern "C" int srb_train_step(const srb_step_desc* s, void* stream) {
     p.g_emb = w.g_emb;
     p.g_l2 = (s->model == SRB_MODEL_LIGHTGCN) ? w.g_l2 : nullptr;
     p.scratch = w.bpr_scratch;
-    SRB_TRY(srb_bpr_l2_fwd_bwd(&p, stream));
+    SRB_TRY(srb_bpr_l2_fwd_bwd(&p, fk ? (void*)fk->side : stream));
+    if (fk) SRB_TRY(check_cuda(cudaEventRecord(fk->join, fk->side), "join record"));
   }
 
   // ---- InfoNCE ----
@@ -401,6 +435,7 @@ extern "C" int srb_train_step(const srb_step_desc* s, void* stream) {
     SRB_TRY(srb_infonce_fwd_bwd(&q, stream));
     n_nce = 1;
   }
+  if (fk) SRB_TRY(check_cuda(cudaStreamWaitEvent(st, fk->join, 0), "join wait"));
   finalize_losses_kernel<<<1, 1, 0, st>>>(w.bpr_losses, w.nce_losses, n_nce, s->cl_rate, s->losses);
   SRB_TRY(post_launch("finalize_losses_kernel"));
 

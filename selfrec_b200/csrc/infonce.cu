@@ -183,6 +183,7 @@ __global__ void __launch_bounds__(256) nce_prep_tc_kernel(const NceArgs a) {
       p.inv1[i] = i1;
       p.inv2[i] = i2;
       p.diag[i] = s12 * a.inv_tau;
+      p.part_l[i] = 0.f;  // softmax denominator l_i, accumulated by pass A
     }
   }
   __syncthreads();
@@ -486,8 +487,9 @@ static int64_t nce_problem_floats(int np, int d) {
   return 14ll * np * d + 4ll * np + 2ll * NCE_MAX_SPLITS * np + 64;  // + lse[np]
 }
 
-// finish for the tensor-core path: dVhat = D + (P_ii - 1) * w/(n tau) * vhat_other (exact fp32), then the
-// same normalisation backward as nce_finish_kernel
+// finish for the tensor-core path: pass A left dV1 unnormalised (sum_j exp(S_ij - 1/tau) v2_j) and the
+// denominators l_i in part_l; dV1hat = w/(n tau l_i) dV1, both sides get the diagonal term
+// (P_ii - 1) * w/(n tau) * vhat_other in exact fp32, then the same normalisation backward as nce_finish_kernel
 __global__ void __launch_bounds__(256) nce_tc_finish_kernel(const NceArgs a) {
   constexpr int D = 64;
   const NceProblem& p = a.p[blockIdx.y];
@@ -496,8 +498,10 @@ __global__ void __launch_bounds__(256) nce_tc_finish_kernel(const NceArgs a) {
   const int n = nce_n(p);
   if (blockIdx.x == 0 && threadIdx.x == 0) *p.loss = (n > 0) ? *p.loss_acc / (float)n : 0.f;
   if (i >= n) return;
-  const float pii = expf(p.diag[i] - p.lse[i]);
-  const float cd = (pii - 1.f) * p.weight * a.inv_tau / (float)n;
+  const float li = p.part_l[i];
+  const float pii = expf(p.diag[i] - a.inv_tau) / li;
+  const float gs = p.weight * a.inv_tau / (float)n;
+  const float cd = (pii - 1.f) * gs;
   const float2 v1 = *reinterpret_cast<const float2*>(p.V1 + (size_t)i * D + lane * 2);
   const float2 v2 = *reinterpret_cast<const float2*>(p.V2 + (size_t)i * D + lane * 2);
 #pragma unroll 1
@@ -505,6 +509,7 @@ __global__ void __launch_bounds__(256) nce_tc_finish_kernel(const NceArgs a) {
     const float2 vh = side ? v2 : v1;
     const float2 vo = side ? v1 : v2;
     float2 dv = *reinterpret_cast<const float2*>((side ? p.dV2 : p.dV1) + (size_t)i * D + lane * 2);
+    if (side == 0) dv.x *= gs / li, dv.y *= gs / li;
     dv.x = fmaf(cd, vo.x, dv.x);
     dv.y = fmaf(cd, vo.y, dv.y);
     const float dot = warp_sum(vh.x * dv.x + vh.y * dv.y);
@@ -525,7 +530,7 @@ static int nce_impl() {
   return impl;
 }
 
-// tensor-core pipeline: prep (exact rows + TF32 hi/lo parts) -> LSE -> GRAD-A -> GRAD-B -> finish
+// tensor-core pipeline: prep (exact rows + TF32 hi/lo parts) -> pass A (LSE + view-1 gradient) -> pass B -> finish
 static int nce_launch_tc(const NceArgs& a, int n_problems, cudaStream_t st) {
   const int np = a.np;
   const int d = NT_D;
@@ -566,9 +571,7 @@ static int nce_launch_tc(const NceArgs& a, int n_problems, cudaStream_t st) {
     o.n_dev = p.n_dev;
     o.weight = p.weight;
     o.diag = p.diag;
-    o.part_m = p.part_m;
-    o.part_l = p.part_l;
-    o.lse = p.lse;
+    o.lsum = p.part_l;  // [np] softmax denominators (first split slice of the partials area)
     o.dV1 = p.dV1;
     o.dV2 = p.dV2;
     o.loss_acc = p.loss_acc;
@@ -587,18 +590,15 @@ static int nce_launch_tc(const NceArgs& a, int n_problems, cudaStream_t st) {
   const size_t smem = NtSmem::total + 1024;
   static bool attr_done = false;
   if (!attr_done) {
-    SRB_TRY(check_cuda(cudaFuncSetAttribute(nce_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "nce tc attr"));
     SRB_TRY(check_cuda(cudaFuncSetAttribute(nce_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "nce tc attr"));
     SRB_TRY(check_cuda(cudaFuncSetAttribute(nce_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "nce tc attr"));
     attr_done = true;
   }
   dim3 grid(row_blocks, splits, n_problems);
-  nce_tc_kernel<0><<<grid, NT_THREADS, smem, st>>>(maps, t);
-  SRB_TRY(post_launch("nce_tc_kernel<lse>"));
   nce_tc_kernel<1><<<grid, NT_THREADS, smem, st>>>(maps, t);
-  SRB_TRY(post_launch("nce_tc_kernel<grad_a>"));
+  SRB_TRY(post_launch("nce_tc_kernel<pass_a>"));
   nce_tc_kernel<2><<<grid, NT_THREADS, smem, st>>>(maps, t);
-  SRB_TRY(post_launch("nce_tc_kernel<grad_b>"));
+  SRB_TRY(post_launch("nce_tc_kernel<pass_b>"));
   {
     dim3 g2((np + 7) / 8, n_problems);
     nce_tc_finish_kernel<<<g2, 256, 0, st>>>(a);

@@ -2,10 +2,12 @@
 //
 // Same contract as infonce.cu (util/loss_torch.py:35-50 + autograd backward); the n x n logit matrix
 // lives only in TMEM / shared memory.  Per problem, with V1, V2 the L2-normalised gathered views:
-//   pass LSE     S = V1 V2^T / tau, tile by tile;  per-row sum of exp(S - 1/tau)   (|S| <= 1/tau: cosines)
-//   pass GRAD-A  rows = view-1 rows i:   G = exp(S - lse_i) * w/(n tau), j != i;   dV1 += G  V2
-//   pass GRAD-B  rows = view-2 rows j:   G'= exp(S^T - lse_i) * w/(n tau), i != j;  dV2 += G' V1
-//   finish       adds the diagonal term (P_ii - 1) w/(n tau) v_i in exact fp32, then the normalisation backward
+//   pass A  rows = view-1 rows i:  E = exp(S - 1/tau)  (|S| <= 1/tau: cosines, so the shift needs no running max);
+//           l_i += sum_j E_ij (the softmax denominator) and, unnormalised, dV1_i += sum_{j != i} E_ij V2_j
+//           -- forward (LSE) and the view-1 gradient in ONE sweep: the 1/l_i factor is applied afterwards
+//   pass B  rows = view-2 rows j:  G' = exp(S^T - lse_i) * w/(n tau), i != j;  dV2 += G' V1   (needs every l_i)
+//   finish  scales dV1 by w/(n tau l_i), adds the diagonal term (P_ii - 1) w/(n tau) v_i in exact fp32, then the
+//           normalisation backward
 // Each CTA owns a block of 128 rows and a strided subset of the 64-column tiles:
 //   warp 0    TMA producer: column-operand tile [64 x 64] (K-major over d, for S; 3-stage ring) and, for the
 //             GRAD passes, the same tile from the transposed copy [64 d x 64 cols] (K-major over the
@@ -55,9 +57,7 @@ struct NtProblem {
   const int32_t* n_dev;
   float weight;
   const float* diag;     // [NP] exact S_ii
-  float* part_m;         // [SPLITS][NP]  (constant 1/tau: the fixed shift)
-  float* part_l;
-  float* lse;            // [NP] combined log-sum-exp of every view-1 row (written by GRAD-A, read by GRAD-B and finish)
+  float* lsum;           // [NP] softmax denominators l_i = sum_j exp(S_ij - 1/tau) (zeroed by prep, accumulated by pass A)
   float* dV1;            // [NP][64] accumulators (zeroed by prep)
   float* dV2;
   float* loss_acc;
@@ -90,7 +90,7 @@ __device__ __forceinline__ float ex2_approx(float x) {  // 2^x, flush-to-zero, 2
   return y;
 }
 
-// mode 0: LSE (rows = view 1)   mode 1: GRAD-A (rows = view 1)   mode 2: GRAD-B (rows = view 2)
+// mode 1: pass A (rows = view 1)   mode 2: pass B (rows = view 2)
 template <int MODE>
 __global__ void __launch_bounds__(NT_THREADS, 1) nce_tc_kernel(const __grid_constant__ NtMaps maps, const NtArgs a) {
   extern __shared__ __align__(1024) uint8_t nt_smem_raw[];
@@ -119,13 +119,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1) nce_tc_kernel(const __grid_cons
   const int lane = threadIdx.x & 31;
   const int n_tiles = (n + NT_C - 1) / NT_C;
   const int my_tiles = (n_tiles - split + a.splits - 1) / a.splits;  // tiles split, split+S, ...
-  if (my_tiles <= 0) {
-    if (MODE == 0 && threadIdx.x < NT_T) {  // an empty split still has to publish neutral partials
-      P.part_m[(size_t)split * a.np + r0 + threadIdx.x] = -INFINITY;
-      P.part_l[(size_t)split * a.np + r0 + threadIdx.x] = 0.f;
-    }
-    return;
-  }
+  if (my_tiles <= 0) return;
   const CUtensorMap* map_row = (MODE == 2) ? maps.v2r[prob] : maps.v1r[prob];    // [2]: hi, lo
   const CUtensorMap* map_col = (MODE == 2) ? maps.v1c[prob] : maps.v2c[prob];
   const CUtensorMap* map_colt = (MODE == 2) ? maps.v1t[prob] : maps.v2t[prob];
@@ -171,7 +165,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1) nce_tc_kernel(const __grid_cons
         for (int h = 0; h < 2; ++h)
           for (int c = 0; c < 2; ++c)
             tma_load_2d(sm + NtSmem::b_off + (s * 2 + h) * NT_BTILE + c * 8192, &map_col[h], bar_full + s, c * 32, t * NT_C);
-        if (MODE != 0) {
+        {
           const int ts = k & 1;
           mbar_wait(bar_tempty + ts, ((k >> 1) & 1) ^ 1);
           mbar_arrive_expect_tx(bar_tfull + ts, 2 * NT_TTILE);
@@ -211,7 +205,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1) nce_tc_kernel(const __grid_cons
       issue_s(0);
       for (int k = 0; k < my_tiles; ++k) {
         if (k + 1 < my_tiles) issue_s(k + 1);  // S of the next tile overlaps the epilogue of this one
-        if (MODE != 0) {
+        {
           const int gs = k & 1;
           const uint32_t bt_base = smem_u32(sm + NtSmem::bt_off + gs * 2 * NT_TTILE);
           const uint32_t g_hi = tmem_g + gs * 128;
@@ -232,7 +226,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1) nce_tc_kernel(const __grid_cons
           umma_commit(bar_tempty + gs);  // transposed tile reusable
         }
       }
-      if (MODE != 0) umma_commit(bar_dfull);
+      umma_commit(bar_dfull);
     }
   } else {
     // ===== epilogue warps: thread = one row of the block x one 32-column half of the tile =====
@@ -246,41 +240,32 @@ __global__ void __launch_bounds__(NT_THREADS, 1) nce_tc_kernel(const __grid_cons
     const float sc = a.inv_tau * L2E;      // exponent scale: 2^(s*sc + off) = e^(s/tau + off/log2(e))
     const float gscale = P.weight * a.inv_tau / (float)n;
     const float lg = log2f(gscale);
-    float l_run = 0.f;        // LSE mode: sum of exp(S - 1/tau) over my columns
-    float off_row = 0.f;      // GRAD-A: -lse_i*log2(e) + log2(gscale)
-    if (MODE == 1) {
-      float M = -INFINITY;
-      for (int s = 0; s < a.splits; ++s) M = fmaxf(M, P.part_m[(size_t)s * a.np + row]);
-      float Ls = 0.f;
-      for (int s = 0; s < a.splits; ++s) {
-        const float ms = P.part_m[(size_t)s * a.np + row];
-        if (ms > -INFINITY) Ls += P.part_l[(size_t)s * a.np + row] * exp2f((ms - M) * L2E);
+    float l_run = 0.f;  // pass A: sum of exp(S - 1/tau) over my columns
+    // pass B: exponent offset of column c = log2(w/(n tau)) - lse_c log2(e), lse_c = 1/tau + ln l_c; the CTAs of the
+    // first row block see every column exactly once and also accumulate the loss = mean(lse_i - S_ii), S_ii exact
+    auto col_const = [&](int col) -> float {
+      float off = -INFINITY, contrib = 0.f;
+      if (col < n) {
+        const float lse = a.inv_tau + logf(P.lsum[col]);
+        off = lg - lse * L2E;
+        contrib = lse - P.diag[col];
       }
-      const float lse_row = row_ok ? M + logf(Ls) : 0.f;
-      off_row = row_ok ? lg - lse_row * L2E : -INFINITY;
-      if (split == 0 && half == 0) {  // loss = mean(lse_i - S_ii), S_ii exact
-        P.lse[row] = lse_row;
-        float contrib = row_ok ? lse_row - P.diag[row] : 0.f;
+      if (blockIdx.x == 0) {
         contrib = warp_sum(contrib);
         if (lane == 0) atomicAdd(P.loss_acc, contrib);
       }
-    }
+      return off;
+    };
     float next_colc = 0.f;
     if (MODE == 2) {  // column constants of tile 0
-      if (et < NT_C) {
-        const int col = split * NT_C + et;
-        colc[et] = (col < n) ? lg - P.lse[col] * L2E : -INFINITY;
-      }
+      if (et < NT_C) colc[et] = col_const(split * NT_C + et);
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
     for (int k = 0; k < my_tiles; ++k) {
       const int t = split + k * a.splits;
       const int s = k & 1;
       const int cb = t * NT_C + half * 32;  // first column of my chunk
-      if (MODE == 2 && et < NT_C && k + 1 < my_tiles) {  // prefetch the next tile's column constants
-        const int col = (t + a.splits) * NT_C + et;
-        next_colc = (col < n) ? lg - P.lse[col] * L2E : -INFINITY;
-      }
+      if (MODE == 2 && et < NT_C && k + 1 < my_tiles) next_colc = col_const((t + a.splits) * NT_C + et);  // prefetch
       mbar_wait(bar_sfull + s, (k >> 1) & 1);
       fence_after_sync();
       uint32_t r[32];
@@ -289,27 +274,19 @@ __global__ void __launch_bounds__(NT_THREADS, 1) nce_tc_kernel(const __grid_cons
       fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_sempty + s);  // S stage drained (values are in registers)
-      if (MODE == 0) {
-        if (cb + 32 <= n) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) l_run += ex2_approx(fmaf(__uint_as_float(r[j]), sc, -sc));
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (cb + j < n) l_run += ex2_approx(fmaf(__uint_as_float(r[j]), sc, -sc));
-        }
-      } else {
-        // G chunk: x = exp(s/tau - lse) * w/(n tau).  The diagonal term (P_ii - 1) v_i is added in exact fp32
-        // by the finish kernel: through the tensor core its TF32 rounding (|G_ii| ~ 1) would dominate the row.
-        // Rows >= n produce values that only reach rows >= n of D, which are never written.
+      {
+        // G chunk: pass A x = exp(s/tau - 1/tau), pass B x = exp(s/tau - lse_col) * w/(n tau).  The diagonal term
+        // (P_ii - 1) v_i is added in exact fp32 by the finish kernel: through the tensor core its TF32 rounding
+        // (|G_ii| ~ 1) would dominate the row.  Rows >= n only reach rows >= n of D, which are never written.
         uint32_t lo[32];
         const float* cc = colc + (k & 1) * NT_C + half * 32;
         const bool edge = (MODE == 1 && cb + 32 > n) || (row >= cb && row < cb + 32);
         if (!edge) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float off = (MODE == 1) ? off_row : cc[j];
+            const float off = (MODE == 1) ? -sc : cc[j];
             const float x = ex2_approx(fmaf(__uint_as_float(r[j]), sc, off));
+            if (MODE == 1) l_run += x;
             const float h = to_tf32_rna(x);
             r[j] = __float_as_uint(h);
             lo[j] = __float_as_uint(x - h);
@@ -317,9 +294,11 @@ __global__ void __launch_bounds__(NT_THREADS, 1) nce_tc_kernel(const __grid_cons
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float off = (MODE == 1) ? off_row : cc[j];
+            const float off = (MODE == 1) ? -sc : cc[j];
             float x = ex2_approx(fmaf(__uint_as_float(r[j]), sc, off));
-            if (cb + j >= n || cb + j == row) x = 0.f;
+            if (cb + j >= n) x = 0.f;
+            if (MODE == 1) l_run += x;  // the denominator includes the diagonal
+            if (cb + j == row) x = 0.f;
             const float h = to_tf32_rna(x);
             r[j] = __float_as_uint(h);
             lo[j] = __float_as_uint(x - h);
@@ -341,16 +320,8 @@ __global__ void __launch_bounds__(NT_THREADS, 1) nce_tc_kernel(const __grid_cons
         }
       }
     }
-    if (MODE == 0) {
-      // the two column halves of a row meet through shared memory (the transposed-tile region is unused in this mode)
-      float* red = reinterpret_cast<float*>(sm + NtSmem::bt_off);
-      if (half == 1) red[row_l] = l_run;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (half == 0 && row < a.np) {
-        P.part_m[(size_t)split * a.np + row] = a.inv_tau;
-        P.part_l[(size_t)split * a.np + row] = l_run + red[row_l];
-      }
-    } else {
+    {
+      if (MODE == 1 && row_ok) atomicAdd(P.lsum + row, l_run);
       mbar_wait(bar_dfull, 0);
       fence_after_sync();
       float* out = ((MODE == 1) ? P.dV1 : P.dV2) + (size_t)row * NT_D + half * 32;

@@ -15,6 +15,19 @@ from . import _lib, ops
 from .util.sampler import NativePairSampler
 
 
+class LossHandle:
+    """Pinned-memory copy of a step's [rec, l2, cl, total] losses; get() waits for the D2H copy."""
+
+    __slots__ = ("_buf", "_ev")
+
+    def __init__(self, buf, ev):
+        self._buf, self._ev = buf, ev
+
+    def get(self):
+        self._ev.synchronize()
+        return self._buf.numpy().copy()
+
+
 class TrainEngine:
     def __init__(self, model, data, emb_size, n_layers, batch_size, lr, reg, *, eps=0.0, tau=0.2, cl_rate=0.0,
                  layer_cl=0, l2_div=1.0, device=None, init_user=None, init_item=None, philox_seed=0x5EED):
@@ -45,6 +58,8 @@ class TrainEngine:
         self.ring = [torch.zeros(self.words, dtype=torch.int32).pin_memory() for _ in range(8)]
         self.ring_ev = [None] * len(self.ring)
         self.ring_pos = 0
+        self.loss_ring = [torch.zeros(4, dtype=torch.float32).pin_memory() for _ in range(8)]
+        self.loss_pos = 0
         ws_bytes = lib.srb_step_workspace_bytes(self.model_id, self.N, self.d, self.B)
         self.workspace = torch.empty(ws_bytes + 256, device=dev, dtype=torch.uint8)
         ws_ptr = (self.workspace.data_ptr() + 255) // 256 * 256
@@ -89,6 +104,7 @@ class TrainEngine:
             raise ValueError(f"noise must be [{views}, {self.L}, {self.N}, {self.d}]")
         self.noise = noise
         self.desc.noise_mode, self.desc.noise = 1, ops._p(noise)
+        self.graph = None  # the step sequence changed: a captured graph is stale
 
     def set_view_graphs(self, adj1, adj2):
         """SGL: the two dropped, re-normalised graphs of this epoch (SGL.py:27-29)."""
@@ -102,8 +118,12 @@ class TrainEngine:
     def _enqueue(self):
         _lib.check(self.lib.srb_train_step(C.byref(self.desc), ops._stream()), "srb_train_step")
 
-    def step(self, batch_words):
-        """batch_words: int32 array/tensor of `words` entries laid out by srb_sampler_next_batch."""
+    def step(self, batch_words, fetch_loss=False):
+        """batch_words: int32 array/tensor of `words` entries laid out by srb_sampler_next_batch.
+        Enqueues the H2D copy and the step (the captured CUDA graph when capture() was called) and
+        returns without synchronising.  fetch_loss=True also enqueues a D2H copy of the four loss
+        values into pinned memory and returns a LossHandle; .get() waits for that copy only, so the
+        caller can sample the next batch while this step runs."""
         slot = self.ring_pos
         self.ring_pos = (slot + 1) % len(self.ring)
         ev = self.ring_ev[slot]
@@ -118,7 +138,18 @@ class TrainEngine:
         ev = torch.cuda.Event()
         ev.record()
         self.ring_ev[slot] = ev
-        self._enqueue()
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._enqueue()
+        if not fetch_loss:
+            return None
+        ls = self.loss_pos
+        self.loss_pos = (ls + 1) % len(self.loss_ring)
+        self.loss_ring[ls].copy_(self.losses, non_blocking=True)
+        lev = torch.cuda.Event()
+        lev.record()
+        return LossHandle(self.loss_ring[ls], lev)
 
     def step_resident(self):
         """Step on whatever batch_dev currently holds (inputs already in HBM)."""

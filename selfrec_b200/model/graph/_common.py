@@ -51,10 +51,13 @@ class FusedGraphModel(GraphRecommender):
         eng = self.engine
         for epoch in range(self.maxEpoch):
             self._epoch_prologue(epoch)
+            if eng.graph is None:
+                eng.capture()  # one CUDA graph launch per batch from here on
             for n, words in enumerate(eng.batches()):
-                eng.step(words)
                 if n % 100 == 0 and n > 0:
-                    self._log_line(epoch, n, eng.losses.tolist())
+                    self._log_line(epoch, n, eng.step(words, fetch_loss=True).get().tolist())
+                else:
+                    eng.step(words)
             with torch.no_grad():
                 self.user_emb, self.item_emb = eng.forward_clean()
             if epoch >= self.EVAL_FROM and epoch % self.EVAL_EVERY == 0:

@@ -418,6 +418,16 @@ def adam_step(p, m, v, g, scalars, beta1=0.9, beta2=0.999, eps=1e-8):
     _lib.check(lib.srb_adam_step(_p(p), _p(m), _p(v), _p(g), p.numel(), _p(scalars), beta1, beta2, eps, _stream()), "srb_adam_step")
 
 
+def scatter_add_segments(dst, segs):
+    """dst[rows + off] += scale * src for up to 8 (src, rows, n_dev, n, off, scale) segments, one launch."""
+    lib = _lib.require_device()
+    arr = (_lib.ScatterSeg * len(segs))()
+    for q, (src, rows, n_dev, n, off, scale) in enumerate(segs):
+        arr[q].src, arr[q].rows, arr[q].n_dev = _p(src), _p(rows), _p(n_dev)
+        arr[q].n, arr[q].row_off, arr[q].scale = int(n), int(off), float(scale)
+    _lib.check(lib.srb_scatter_add_segments(_p(dst), dst.shape[1], len(segs), arr, _stream()), "srb_scatter_add_segments")
+
+
 def scatter_add_rows(dst, src, rows, row_off=0, scale=1.0):
     lib = _lib.require_device()
     rows = _i32(rows, dst.device)
