@@ -166,6 +166,7 @@ class ShardedXSimGCL:
         self.losses = torch.zeros(4, device=dev)
         self.noise = None
         self.gd = torch.zeros((self.N, self.d), device=dev)
+        self._alloc_step_buffers()
         torch.cuda.synchronize()
         p.dist.barrier(p.group)
 
@@ -206,78 +207,112 @@ class ShardedXSimGCL:
         out = fin.clone()
         return out[: self.U], out[self.U:]
 
-    def step(self, words, words_dev=None):
-        """One training step; `words` = batch buffer (srb_sampler_next_batch layout), same on all ranks.
-        words_dev: the same buffer already resident on the device (then only the 3 header ints of the
-        host copy are read)."""
+    def _alloc_step_buffers(self):
+        """Everything a step touches is allocated once: a step then makes no allocation and no host read,
+        so it can be captured in a CUDA graph (counts are read by the kernels from the batch header)."""
         torch, ops, p = self.torch, self.ops, self.prop
         lib = _lib.load()
-        B, d, U, L = self.B, self.d, self.U, self.L
-        w = words_dev if words_dev is not None else torch.as_tensor(np.asarray(words, dtype=np.int32)).to(p.dev)
-        b, nu, ni = (int(x) for x in np.asarray(words[:3]))
-        u_idx, i_idx, j_idx = w[4:4 + b], w[4 + B:4 + B + b], w[4 + 2 * B:4 + 2 * B + b]
-        uq_u, uq_i = w[4 + 3 * B:4 + 3 * B + nu], w[4 + 4 * B:4 + 4 * B + ni]
-        ops.adam_prepare(self.step_dev, self.scalars, self.lr)
-        fin, cl = self._forward(True)
-        # ---- replicated batch losses on the gathered layers ----
-        g_emb = torch.empty((3, b, d), device=p.dev)
-        g_l2 = torch.empty((3, b, d), device=p.dev) if self.model == "LightGCN" else None
-        scratch = torch.empty(8, device=p.dev)
-        bl = torch.empty(2, device=p.dev)
+        B, d, U, dev = self.B, self.d, self.U, p.dev
+        self.words = _lib.BATCH_HEADER + 5 * B
+        self.batch_dev = torch.zeros(self.words, dtype=torch.int32, device=dev)
+        w, H = self.batch_dev, _lib.BATCH_HEADER
+        self._cnt = [w[0:1], w[1:2], w[2:3]]                       # b, n_uniq_u, n_uniq_i (device)
+        self._idx = [w[H + q * B: H + (q + 1) * B] for q in range(5)]  # u, i, j, uniq_u, uniq_i (capacity B)
+        self.g_emb = torch.zeros((3, B, d), device=dev)
+        self.g_l2 = torch.zeros((3, B, d), device=dev) if self.model == "LightGCN" else None
+        self._scratch = torch.zeros(8, device=dev)
+        self._bl = torch.zeros(2, device=dev)
+        self._nl = torch.zeros(2, device=dev)
+        self._gn = [torch.zeros((B, d), device=dev) for _ in range(4)]  # g1 / g2 of the user and item problems
+        fin, cl = p.bufs[self.FIN], p.bufs[self.CL]
+        u_idx, i_idx, j_idx, uq_u, uq_i = self._idx
         bd = _lib.BprDesc()
         bd.emb, bd.n_users, bd.d = ops._p(fin), U, d
         bd.l2_emb = ops._p(p.bufs[self.P]) if self.model == "LightGCN" else ops._p(fin)
-        bd.u_idx, bd.i_idx, bd.j_idx, bd.b = ops._p(u_idx), ops._p(i_idx), ops._p(j_idx), b
+        bd.u_idx, bd.i_idx, bd.j_idx, bd.b_dev, bd.b = ops._p(u_idx), ops._p(i_idx), ops._p(j_idx), ops._p(self._cnt[0]), B
         bd.emb_scale, bd.reg, bd.grad_scale = 1.0, self.reg, 1.0
         bd.l2_terms = 2 if self.model == "XSimGCL" else 3
         bd.l2_div = self.l2_div
-        bd.losses, bd.g_emb, bd.g_l2, bd.scratch = ops._p(bl), ops._p(g_emb), ops._p(g_l2), ops._p(scratch)
-        _lib.check(lib.srb_bpr_l2_fwd_bwd(C.byref(bd), ops._stream()), "srb_bpr_l2_fwd_bwd")
-        cm = 1.0 / (L + 1 if self.model == "LightGCN" else L)
-        final_segs = [(g_emb[0], u_idx, 0), (g_emb[1], i_idx, U), (g_emb[2], j_idx, U)]
-        cl_segs, ego_segs = [], []
-        cl_loss = None
+        bd.losses, bd.g_emb, bd.g_l2, bd.scratch = ops._p(self._bl), ops._p(self.g_emb), ops._p(self.g_l2), ops._p(self._scratch)
+        self._bpr_desc = bd
+        self._nce_desc = None
         if self.model == "XSimGCL":
-            nl, outs = ops.infonce_raw(
-                [dict(table1=fin, table2=cl, idx=uq_u, n=nu, weight=self.cl_rate),
-                 dict(table1=fin, table2=cl, idx=uq_i, n=ni, weight=self.cl_rate, row_off1=U, row_off2=U)], d, self.tau)
-            cl_loss = nl
-            final_segs += [(outs[0][0], uq_u, 0), (outs[1][0], uq_i, U)]
-            tgt = cl_segs if 1 <= self.layer_cl <= L else ego_segs
-            tgt += [(outs[0][1], uq_u, 0), (outs[1][1], uq_i, U)]
+            ws_bytes = lib.srb_infonce_workspace_bytes(B, d, 2)
+            self._nce_ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+            nd = _lib.InfoNceDesc()
+            nd.n_problems, nd.d, nd.b_cos, nd.temperature = 2, d, 1, float(self.tau)
+            for q, (idx, cnt, off) in enumerate(((uq_u, self._cnt[1], 0), (uq_i, self._cnt[2], U))):
+                pr = nd.prob[q]
+                pr.table1, pr.table2, pr.row_off1, pr.row_off2 = ops._p(fin), ops._p(cl), off, off
+                pr.scale1, pr.scale2 = 1.0, 1.0
+                pr.idx, pr.n_dev, pr.n, pr.weight = ops._p(idx), ops._p(cnt), B, float(self.cl_rate)
+                pr.g1, pr.g2 = ops._p(self._gn[2 * q]), ops._p(self._gn[2 * q + 1])
+                pr.loss = C.c_void_p(self._nl.data_ptr() + 4 * q)
+            nd.workspace, nd.workspace_bytes = ops._p(self._nce_ws), ws_bytes
+            self._nce_desc = nd
+        cm = 1.0 / (self.L + 1 if self.model == "LightGCN" else self.L)
+        b_dev, nu_dev, ni_dev = self._cnt
+        self._final_segs = [(self.g_emb[0], u_idx, b_dev, B, 0, cm), (self.g_emb[1], i_idx, b_dev, B, U, cm),
+                            (self.g_emb[2], j_idx, b_dev, B, U, cm)]
+        self._cl_segs, self._ego_segs = [], []
+        if self.model == "XSimGCL":
+            self._final_segs += [(self._gn[0], uq_u, nu_dev, B, 0, cm), (self._gn[2], uq_i, ni_dev, B, U, cm)]
+            tgt = self._cl_segs if 1 <= self.layer_cl <= self.L else self._ego_segs
+            tgt += [(self._gn[1], uq_u, nu_dev, B, 0, 1.0), (self._gn[3], uq_i, ni_dev, B, U, 1.0)]
         else:
-            ego_segs += [(g_l2[0], u_idx, 0), (g_l2[1], i_idx, U), (g_l2[2], j_idx, U)]
-        # ---- Horner backward, rows sharded, every level pushed to all ranks ----
-        def scatter(dst, segs, scale):
-            for src, rows, off in segs:
-                ops.scatter_add_rows(dst, src, rows, off, scale)
+            self._ego_segs += [(self.g_l2[0], u_idx, b_dev, B, 0, 1.0), (self.g_l2[1], i_idx, b_dev, B, U, 1.0),
+                               (self.g_l2[2], j_idx, b_dev, B, U, 1.0)]
 
+    def step(self, words=None, words_dev=None):
+        """One training step; the batch buffer (srb_sampler_next_batch layout) must be the same on all ranks.
+        words: host buffer (copied to the device), or words_dev: the buffer already resident on the device."""
+        torch = self.torch
+        if words_dev is not None:
+            self.batch_dev.copy_(words_dev, non_blocking=True)
+        elif words is not None:
+            self.batch_dev.copy_(torch.as_tensor(np.asarray(words, dtype=np.int32)), non_blocking=True)
+        self.step_resident()
+
+    def step_resident(self):
+        """Step on whatever self.batch_dev holds: no allocation, no host read (CUDA-graph capturable)."""
+        torch, ops, p = self.torch, self.ops, self.prop
+        lib = _lib.load()
+        L = self.L
+        ops.adam_prepare(self.step_dev, self.scalars, self.lr)
+        self._forward(True)
+        # ---- replicated batch losses on the gathered layers ----
+        _lib.check(lib.srb_bpr_l2_fwd_bwd(C.byref(self._bpr_desc), ops._stream()), "srb_bpr_l2_fwd_bwd")
+        if self._nce_desc is not None:
+            _lib.check(lib.srb_infonce_fwd_bwd(C.byref(self._nce_desc), ops._stream()), "srb_infonce_fwd_bwd")
+        # ---- Horner backward, rows sharded, every level pushed to all ranks ----
+        final_segs, cl_segs, ego_segs = self._final_segs, self._cl_segs, self._ego_segs
         acc = p.bufs[self.A0]
         acc.zero_()
-        scatter(acc, final_segs, cm)
-        if self.layer_cl == L:
-            scatter(acc, cl_segs, 1.0)
+        ops.scatter_add_segments(acc, final_segs + (cl_segs if self.layer_cl == L else []))
         x_idx = self.A0
         for k in range(L - 1, 0, -1):
             y_idx = self.A1 if x_idx == self.A0 else self.A0
             p.spmm(p.bufs[x_idx], push_y=y_idx)
             p.barrier()
-            y = p.bufs[y_idx]
-            scatter(y, final_segs, cm)  # replicated: every rank adds the same sparse rows to its copy
-            if self.layer_cl == k:
-                scatter(y, cl_segs, 1.0)
+            # replicated: every rank adds the same sparse rows to its copy
+            ops.scatter_add_segments(p.bufs[y_idx], final_segs + (cl_segs if self.layer_cl == k else []))
             x_idx = y_idx
         extra = None
         if self.model == "LightGCN" or ego_segs:
             self.gd.zero_()
-            if self.model == "LightGCN":
-                scatter(self.gd, final_segs, cm)
-            scatter(self.gd, ego_segs, 1.0)
+            ops.scatter_add_segments(self.gd, (final_segs if self.model == "LightGCN" else []) + ego_segs)
             extra = self.gd
         epi = dict(adam_p=p.bufs[self.P], adam_m=self.m, adam_v=self.v, adam_scalars=self.scalars, beta1=0.9, beta2=0.999, adam_eps=1e-8)
         if extra is not None:
             epi["extra"] = extra
         p.spmm(p.bufs[x_idx], push_p=self.P, **epi)
         p.barrier()
-        cl_val = (self.cl_rate * cl_loss.sum()) if cl_loss is not None else torch.zeros((), device=p.dev)
-        self.losses = torch.stack([bl[0], bl[1], cl_val, bl[0] + bl[1] + cl_val])
+        ls = self.losses
+        ls[0:2].copy_(self._bl)
+        if self._nce_desc is not None:
+            torch.add(self._nl[0:1], self._nl[1:2], out=ls[2:3])
+            ls[2:3].mul_(self.cl_rate)
+        else:
+            ls[2:3].zero_()
+        torch.add(ls[0:1], ls[1:2], out=ls[3:4])
+        ls[3:4].add_(ls[2:3])
