@@ -34,6 +34,25 @@ CFG = dict(model="XSimGCL", shape="yelp2018", d=64, L=3, B=2048, tau=0.2, lam=0.
 METRIC = "XSimGCL yelp2018 train steps/sec"
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout: libraries that write banners to fd 1 (NCCL's version line) are
+    pointed at stderr for the whole run, and the JSON line goes to the saved descriptor."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -156,7 +175,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "rank": {"value": len(sample) * data.item_num / rdt, "unit": "items/s", "sample": f"{len(sample)} of {data.user_num} users"},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------
@@ -199,7 +218,7 @@ def run_ours(args, rank, world, local_rank):
         ops.score_topk(ue, ie, torch.arange(eng.U, device=dev, dtype=torch.int32), torch.from_numpy(rp).to(dev),
                        torch.from_numpy(ri).to(dev), 20)
         torch.cuda.synchronize()
-        print(json.dumps({"profile_mode": True, "launches": _lib.launch_count()}))
+        emit({"profile_mode": True, "launches": _lib.launch_count()})
         return
 
     # launches per step (eager), then capture
@@ -356,7 +375,7 @@ def run_ours(args, rank, world, local_rank):
         "cpu_baseline": cpu,
         "loss": [float(v) for v in loss_host.tolist()],
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_sharded(args, rank, world, local_rank, data):
@@ -475,7 +494,7 @@ def run_sharded(args, rank, world, local_rank, data):
         "cpu_baseline": None,
         "loss": [float(v) for v in loss_host.tolist()],
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def cpu_baseline(data, args):
@@ -517,6 +536,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--profile", action="store_true", help="eager steps only, for ncu (never a bench value)")
     args = ap.parse_args()
+    claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -303,6 +303,45 @@ int srb_topk_rows(const float* scores, int32_t n_q, int32_t n_items, int32_t k, 
                   float* out_scores, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Native dataset -> CSR builder (host C++).  Replaces the Python loops of
+ *   FileIO.load_data_set (data/loader.py:23-33), Interaction.__generate_set (data/ui_graph.py:29-45),
+ *   __create_sparse_bipartite_adjacency / __create_sparse_interaction_matrix (data/ui_graph.py:47-72)
+ *   and the scaling half of normalize_graph_mat (data/graph.py:16-18)
+ * with identical results: ids in order of first appearance in the training file, duplicate lines
+ * summed, test pairs kept only when both user and item are known, adjacency values the fp32
+ * products (d[r] * a) * d[c].  A malformed line fails the load (the reference raises IndexError /
+ * ValueError there).  Handles are host objects; nothing here touches the GPU.
+ * ------------------------------------------------------------------------------------- */
+typedef struct srb_dataset srb_dataset;
+srb_dataset* srb_dataset_load(const char* train_path, const char* test_path /* may be NULL */);
+void srb_dataset_free(srb_dataset* d);
+/* out[8] = n_users, n_items, n_train_lines, n_test_pairs_kept, n_distinct_train_pairs,
+ *          total bytes of user names, total bytes of item names, n_test_lines (kept or not) */
+int srb_dataset_counts(const srb_dataset* d, int64_t* out);
+/* names of ids 0..n-1 (which: 0 users, 1 items), concatenated; offsets[n+1] */
+int srb_dataset_names(const srb_dataset* d, int32_t which, char* blob, int64_t* offsets);
+/* (user id, item id, weight) in file order; which: 0 training lines, 1 kept test lines */
+int srb_dataset_pairs(const srb_dataset* d, int32_t which, int32_t* u, int32_t* i, double* w);
+/* users x items, duplicates summed, columns ascending: rowptr[U+1], colidx/vals[n_distinct] */
+int srb_dataset_interaction_csr(const srb_dataset* d, int32_t* rowptr, int32_t* colidx, float* vals);
+/* (U+I) x (U+I) bipartite adjacency, rows = users then items, columns ascending:
+ * rowptr[N+1], colidx/vals[2 n_distinct].  d_inv == NULL: raw counts; else vals = (d_inv[r]*a)*d_inv[c].
+ * rowsum (optional, [N]) receives the fp32 row sums of the raw counts. */
+int srb_dataset_adjacency_csr(const srb_dataset* d, const float* d_inv, int32_t* rowptr,
+                              int32_t* colidx, float* vals, float* rowsum);
+
+/* ---------------------------------------------------------------------------------------
+ * Ranking metrics, device part (util/evaluation.py:9-15 `hits`, :85-97 NDCG):
+ * hit_mask[q] bit r = 1 iff topk_ids[q, r] is in the test set of users[q]  (r < k <= 64).
+ * test_ptr / test_idx: CSR over user ids of the test items that have a training id, sorted per
+ * user.  Hit Ratio / Precision / Recall / NDCG follow on the host from the masks with the
+ * reference's own float expressions (selfrec_b200/util/evaluation.py), so they match bit for bit.
+ * ------------------------------------------------------------------------------------- */
+int srb_rank_hit_masks(const int32_t* topk_ids, int32_t n_q, int32_t k, const int32_t* users,
+                       const int32_t* test_ptr, const int32_t* test_idx, uint64_t* hit_mask,
+                       void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * One whole training step (R3-R8, R10) as a single call: forward propagation, gather +
  * BPR + L2, InfoNCE, Horner backward through the propagation, Adam in the epilogue of the
  * last backward SpMM.  Replaces the body of <Model>.train()'s batch loop:

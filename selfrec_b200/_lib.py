@@ -122,6 +122,14 @@ SYMBOLS = {
     "srb_l2_reg_bwd": (C.c_int, [C.c_int32, C.POINTER(VP), C.POINTER(VP), c_i64p, c_i32p, C.c_float, VP, VP, VP]),
     "srb_scatter_add_rows": (C.c_int, [VP, C.c_int32, VP, VP, C.c_int32, VP, C.c_int32, C.c_float, VP]),
     "srb_scatter_add_segments": (C.c_int, [VP, C.c_int32, C.c_int32, VP, VP]),
+    "srb_rank_hit_masks": (C.c_int, [VP, C.c_int32, C.c_int32, VP, VP, VP, VP, VP]),
+    "srb_dataset_load": (VP, [C.c_char_p, C.c_char_p]),
+    "srb_dataset_free": (None, [VP]),
+    "srb_dataset_counts": (C.c_int, [VP, VP]),
+    "srb_dataset_names": (C.c_int, [VP, C.c_int32, VP, VP]),
+    "srb_dataset_pairs": (C.c_int, [VP, C.c_int32, VP, VP, VP]),
+    "srb_dataset_interaction_csr": (C.c_int, [VP, VP, VP, VP]),
+    "srb_dataset_adjacency_csr": (C.c_int, [VP, VP, VP, VP, VP, VP]),
     "srb_adam_prepare": (C.c_int, [VP, VP, C.c_double, C.c_double, C.c_double, VP]),
     "srb_adam_step": (C.c_int, [VP, VP, VP, VP, C.c_int64, VP, C.c_double, C.c_double, C.c_float, VP]),
     "srb_topk_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),

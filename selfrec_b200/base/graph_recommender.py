@@ -16,7 +16,7 @@ import torch
 from .. import ops
 from ..data.loader import FileIO
 from ..data.ui_graph import Interaction
-from ..util.evaluation import ranking_evaluation
+from ..util.evaluation import ranking_evaluation, ranking_evaluation_from_masks
 from .recommender import Recommender
 
 
@@ -99,10 +99,24 @@ class GraphRecommender(Recommender):
         FileIO.write_file(out_dir, f"{name}@{stamp}-performance.txt", self.result)
         print(f"The result of {self.model_name}:\n{''.join(self.result)}")
 
+    def _fast_measure(self):
+        """fast_evaluation's metrics without leaving id space: full-catalog top-k on the device, hit masks on
+        the device (srb_rank_hit_masks), the reference's float expressions on the masks.  Same strings as
+        ranking_evaluation(self.data.test_set, self.test(), [self.max_N])."""
+        data = self.data
+        names = list(data.test_set)
+        if not (self._has_embedding_tables() and self.max_N <= 64 and all(u in data.user for u in names)):
+            return ranking_evaluation(data.test_set, self.test(), [self.max_N])
+        uids = np.fromiter((data.user[u] for u in names), dtype=np.int32, count=len(names))
+        rated_ptr, rated_idx = data.rated_csr()
+        ids, _ = ops.score_topk(self.user_emb.detach(), self.item_emb.detach(), uids, rated_ptr, rated_idx, self.max_N)
+        test_ptr, test_idx, n_test = data.test_csr()
+        masks = ops.rank_hit_masks(ids, uids, test_ptr, test_idx).cpu().numpy()
+        return ranking_evaluation_from_masks(n_test[uids], masks.view(np.uint64), [self.max_N])
+
     def fast_evaluation(self, epoch):
         print("Evaluating the model...")
-        rec_list = self.test()
-        measure = ranking_evaluation(self.data.test_set, rec_list, [self.max_N])
+        measure = self._fast_measure()
         performance = {k: float(v) for m in measure[1:] for k, v in [m.strip().split(":")]}
         if self.bestPerformance:
             # strictly more metrics improved than worsened (graph_recommender.py:88-92)

@@ -1,0 +1,334 @@
+// Native dataset -> CSR builder: the host-side work of
+//   FileIO.load_data_set        data/loader.py:23-33      `user item weight` per line
+//   Interaction.__generate_set  data/ui_graph.py:29-45    first-appearance ids, test filtering
+//   __create_sparse_*           data/ui_graph.py:47-72    bipartite adjacency / interaction matrix
+//   normalize_graph_mat         data/graph.py:10-24       D^-1/2 A D^-1/2 in fp32
+// without Python dict loops (4.1 s + 3.4 s at yelp2018; infeasible at 2e8 edges).  Same results:
+// ids in order of first appearance in the training file, duplicate lines summed, test pairs kept only
+// when user AND item are known, every adjacency value the fp32 product (d[r] * a) * d[c].  The one piece
+// left to numpy is d = rowsum^-0.5 (an N-vector): numpy's float32 pow is what the reference calls and
+// libm's powf is not guaranteed to round identically.
+#include <algorithm>
+#include <cerrno>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <string_view>
+#include <unordered_map>
+#include <vector>
+
+#include "selfrec_b200.h"
+
+namespace srb {
+void set_error(const char* fmt, ...);
+}
+
+struct srb_dataset {
+  std::vector<char> train_buf, test_buf;                 // file contents (names are views into these)
+  std::vector<std::string_view> user_names, item_names;  // id -> name
+  std::vector<int32_t> tr_u, tr_i, te_u, te_i;           // pairs in file order
+  std::vector<double> tr_w, te_w;
+  int64_t n_test_lines = 0;                              // all test lines, kept or not
+  // interaction matrix (users x items), duplicates summed, columns ascending
+  std::vector<int32_t> r_ptr, r_col;
+  std::vector<float> r_val;
+  // its transpose (items x users)
+  std::vector<int32_t> t_ptr, t_col;
+  std::vector<float> t_val;
+};
+
+namespace {
+
+bool read_file(const char* path, std::vector<char>& out) {
+  FILE* f = fopen(path, "rb");
+  if (!f) {
+    srb::set_error("dataset: cannot open %s: %s", path, strerror(errno));
+    return false;
+  }
+  fseek(f, 0, SEEK_END);
+  const long n = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  out.resize(n > 0 ? (size_t)n : 0);
+  const size_t got = out.empty() ? 0 : fread(out.data(), 1, out.size(), f);
+  fclose(f);
+  if (got != out.size()) {
+    srb::set_error("dataset: short read on %s", path);
+    return false;
+  }
+  return true;
+}
+
+inline bool py_space(char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\n' || c == '\v' || c == '\f'; }
+
+struct Triple {
+  std::string_view u, i;
+  double w;
+};
+
+// one line the way the reference reads it: line.strip().split(' ') -> parts[0], parts[1], float(parts[2])
+// returns 0 ok, 1 malformed
+int parse_line(const char* b, const char* e, Triple& t) {
+  while (b < e && py_space(*b)) ++b;
+  while (e > b && py_space(e[-1])) --e;
+  const char* p = b;
+  const char* f[3][2];
+  int nf = 0;
+  while (nf < 3) {
+    const char* s = p;
+    while (p < e && *p != ' ') ++p;
+    f[nf][0] = s;
+    f[nf][1] = p;
+    ++nf;
+    if (p >= e) break;
+    ++p;  // the single separating space (consecutive spaces yield empty fields, as str.split(' ') does)
+  }
+  if (nf < 3) return 1;
+  t.u = std::string_view(f[0][0], (size_t)(f[0][1] - f[0][0]));
+  t.i = std::string_view(f[1][0], (size_t)(f[1][1] - f[1][0]));
+  std::string num(f[2][0], (size_t)(f[2][1] - f[2][0]));
+  if (num.empty()) return 1;
+  char* endp = nullptr;
+  errno = 0;
+  t.w = strtod(num.c_str(), &endp);  // correctly rounded, like float()
+  while (endp && *endp && py_space(*endp)) ++endp;
+  if (!endp || *endp != '\0') return 1;
+  return 0;
+}
+
+template <class F>
+bool for_each_line(const std::vector<char>& buf, const char* what, F&& fn) {
+  const char* p = buf.data();
+  const char* end = p + buf.size();
+  long line_no = 0;
+  while (p < end) {
+    const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
+    const char* le = nl ? nl : end;
+    ++line_no;
+    Triple t;
+    if (parse_line(p, le, t)) {
+      srb::set_error("dataset: %s line %ld is not `user item weight`", what, line_no);
+      return false;
+    }
+    fn(t);
+    p = nl ? nl + 1 : end;
+  }
+  return true;
+}
+
+// CSR of (rows, cols) with duplicate pairs summed, columns ascending: counting sort by row, then an
+// in-row sort (rows are short: insertion sort below 32 entries, std::sort above)
+void build_csr(int n_rows, const std::vector<int32_t>& rows, const std::vector<int32_t>& cols, std::vector<int32_t>& ptr,
+               std::vector<int32_t>& col, std::vector<float>& val) {
+  const size_t nnz = rows.size();
+  std::vector<int64_t> start((size_t)n_rows + 1, 0);
+  for (size_t k = 0; k < nnz; ++k) ++start[(size_t)rows[k] + 1];
+  for (int r = 0; r < n_rows; ++r) start[(size_t)r + 1] += start[r];
+  std::vector<int32_t> tmp(nnz);
+  {
+    std::vector<int64_t> fill(start.begin(), start.end() - 1);
+    for (size_t k = 0; k < nnz; ++k) tmp[(size_t)fill[rows[k]]++] = cols[k];
+  }
+  ptr.assign((size_t)n_rows + 1, 0);
+  col.clear();
+  val.clear();
+  col.reserve(nnz);
+  val.reserve(nnz);
+  for (int r = 0; r < n_rows; ++r) {
+    int32_t* b = tmp.data() + start[r];
+    int32_t* e = tmp.data() + start[(size_t)r + 1];
+    if (e - b < 32) {
+      for (int32_t* p = b + 1; p < e; ++p) {
+        const int32_t x = *p;
+        int32_t* q = p;
+        while (q > b && q[-1] > x) {
+          *q = q[-1];
+          --q;
+        }
+        *q = x;
+      }
+    } else {
+      std::sort(b, e);
+    }
+    for (int32_t* p = b; p < e;) {
+      int32_t* q = p;
+      float s = 0.f;
+      while (q < e && *q == *p) {
+        s += 1.0f;  // scipy sums the duplicate ones in fp32
+        ++q;
+      }
+      col.push_back(*p);
+      val.push_back(s);
+      p = q;
+    }
+    ptr[(size_t)r + 1] = (int32_t)col.size();
+  }
+}
+
+}  // namespace
+
+extern "C" srb_dataset* srb_dataset_load(const char* train_path, const char* test_path) {
+  if (!train_path) {
+    srb::set_error("dataset: null training path");
+    return nullptr;
+  }
+  srb_dataset* d = new srb_dataset();
+  if (!read_file(train_path, d->train_buf) || (test_path && !read_file(test_path, d->test_buf))) {
+    delete d;
+    return nullptr;
+  }
+  std::unordered_map<std::string_view, int32_t> umap, imap;
+  umap.reserve(1 << 16);
+  imap.reserve(1 << 16);
+  const size_t guess = d->train_buf.size() / 12 + 16;
+  d->tr_u.reserve(guess);
+  d->tr_i.reserve(guess);
+  d->tr_w.reserve(guess);
+  bool ok = for_each_line(d->train_buf, "training file", [&](const Triple& t) {
+    auto iu = umap.find(t.u);
+    int32_t uid;
+    if (iu == umap.end()) {
+      uid = (int32_t)d->user_names.size();
+      umap.emplace(t.u, uid);
+      d->user_names.push_back(t.u);
+    } else {
+      uid = iu->second;
+    }
+    auto ii = imap.find(t.i);
+    int32_t iid;
+    if (ii == imap.end()) {
+      iid = (int32_t)d->item_names.size();
+      imap.emplace(t.i, iid);
+      d->item_names.push_back(t.i);
+    } else {
+      iid = ii->second;
+    }
+    d->tr_u.push_back(uid);
+    d->tr_i.push_back(iid);
+    d->tr_w.push_back(t.w);
+  });
+  if (ok && test_path)
+    ok = for_each_line(d->test_buf, "test file", [&](const Triple& t) {
+      ++d->n_test_lines;
+      auto iu = umap.find(t.u);
+      auto ii = imap.find(t.i);
+      if (iu == umap.end() || ii == imap.end()) return;  // ui_graph.py:43: unseen users / items are dropped
+      d->te_u.push_back(iu->second);
+      d->te_i.push_back(ii->second);
+      d->te_w.push_back(t.w);
+    });
+  if (!ok) {
+    delete d;
+    return nullptr;
+  }
+  if (d->tr_u.size() > (size_t)INT32_MAX) {
+    srb::set_error("dataset: more than 2^31-1 training lines");
+    delete d;
+    return nullptr;
+  }
+  const int U = (int)d->user_names.size(), I = (int)d->item_names.size();
+  build_csr(U, d->tr_u, d->tr_i, d->r_ptr, d->r_col, d->r_val);
+  build_csr(I, d->tr_i, d->tr_u, d->t_ptr, d->t_col, d->t_val);
+  return d;
+}
+
+extern "C" void srb_dataset_free(srb_dataset* d) { delete d; }
+
+extern "C" int srb_dataset_counts(const srb_dataset* d, int64_t* out) {
+  if (!d || !out) {
+    srb::set_error("dataset: null pointer");
+    return SRB_ERR_ARG;
+  }
+  int64_t ub = 0, ib = 0;
+  for (auto& s : d->user_names) ub += (int64_t)s.size();
+  for (auto& s : d->item_names) ib += (int64_t)s.size();
+  out[0] = (int64_t)d->user_names.size();
+  out[1] = (int64_t)d->item_names.size();
+  out[2] = (int64_t)d->tr_u.size();
+  out[3] = (int64_t)d->te_u.size();
+  out[4] = (int64_t)d->r_col.size();  // distinct (user, item) pairs
+  out[5] = ub;
+  out[6] = ib;
+  out[7] = d->n_test_lines;
+  return SRB_OK;
+}
+
+extern "C" int srb_dataset_names(const srb_dataset* d, int32_t which, char* blob, int64_t* offsets) {
+  if (!d || !blob || !offsets || (which != 0 && which != 1)) {
+    srb::set_error("dataset_names: bad argument");
+    return SRB_ERR_ARG;
+  }
+  const auto& v = which ? d->item_names : d->user_names;
+  int64_t o = 0;
+  for (size_t k = 0; k < v.size(); ++k) {
+    offsets[k] = o;
+    memcpy(blob + o, v[k].data(), v[k].size());
+    o += (int64_t)v[k].size();
+  }
+  offsets[v.size()] = o;
+  return SRB_OK;
+}
+
+extern "C" int srb_dataset_pairs(const srb_dataset* d, int32_t which, int32_t* u, int32_t* i, double* w) {
+  if (!d || !u || !i || !w || (which != 0 && which != 1)) {
+    srb::set_error("dataset_pairs: bad argument");
+    return SRB_ERR_ARG;
+  }
+  const auto& su = which ? d->te_u : d->tr_u;
+  const auto& si = which ? d->te_i : d->tr_i;
+  const auto& sw = which ? d->te_w : d->tr_w;
+  if (!su.empty()) {
+    memcpy(u, su.data(), su.size() * 4);
+    memcpy(i, si.data(), si.size() * 4);
+    memcpy(w, sw.data(), sw.size() * 8);
+  }
+  return SRB_OK;
+}
+
+extern "C" int srb_dataset_interaction_csr(const srb_dataset* d, int32_t* rowptr, int32_t* colidx, float* vals) {
+  if (!d || !rowptr || !colidx || !vals) {
+    srb::set_error("dataset_interaction_csr: null pointer");
+    return SRB_ERR_ARG;
+  }
+  memcpy(rowptr, d->r_ptr.data(), d->r_ptr.size() * 4);
+  if (!d->r_col.empty()) {
+    memcpy(colidx, d->r_col.data(), d->r_col.size() * 4);
+    memcpy(vals, d->r_val.data(), d->r_val.size() * 4);
+  }
+  return SRB_OK;
+}
+
+extern "C" int srb_dataset_adjacency_csr(const srb_dataset* d, const float* d_inv, int32_t* rowptr, int32_t* colidx, float* vals,
+                                         float* rowsum) {
+  if (!d || !rowptr || !colidx || !vals) {
+    srb::set_error("dataset_adjacency_csr: null pointer");
+    return SRB_ERR_ARG;
+  }
+  const int U = (int)d->user_names.size(), I = (int)d->item_names.size();
+  int64_t o = 0;
+  rowptr[0] = 0;
+  for (int r = 0; r < U + I; ++r) {
+    const bool is_user = r < U;
+    const int lr = is_user ? r : r - U;
+    const std::vector<int32_t>& ptr = is_user ? d->r_ptr : d->t_ptr;
+    const std::vector<int32_t>& col = is_user ? d->r_col : d->t_col;
+    const std::vector<float>& val = is_user ? d->r_val : d->t_val;
+    float rs = 0.f;
+    for (int32_t p = ptr[lr]; p < ptr[(size_t)lr + 1]; ++p) {
+      const int32_t c = is_user ? col[p] + U : col[p];
+      float v = val[p];
+      rs += v;
+      if (d_inv) {
+        v = d_inv[r] * v;  // diags(d).dot(A): one fp32 product per entry ...
+        v = v * d_inv[c];  // ... then .dot(diags(d)): a second one (data/graph.py:16-18)
+      }
+      colidx[o] = c;
+      vals[o] = v;
+      ++o;
+    }
+    rowptr[(size_t)r + 1] = (int32_t)o;
+    if (rowsum) rowsum[r] = rs;
+  }
+  return SRB_OK;
+}

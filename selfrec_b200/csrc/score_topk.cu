@@ -405,3 +405,43 @@ extern "C" int srb_score_rows(const float* user_emb, const float* item_emb, int3
   }
   return srb::post_launch("score_rows_kernel");
 }
+
+namespace srb {
+// one warp per query row: lane r (and r + 32) looks its recommended id up in the user's sorted test list
+__global__ void __launch_bounds__(256) rank_hit_masks_kernel(const int32_t* __restrict__ ids, int n_q, int k, const int32_t* __restrict__ users,
+                                                             const int32_t* __restrict__ test_ptr, const int32_t* __restrict__ test_idx,
+                                                             unsigned long long* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= n_q) return;
+  const int u = users[q];
+  const int beg = test_ptr[u], end = test_ptr[u + 1];
+  unsigned long long mask = 0;
+  for (int half = 0; half < 2; ++half) {
+    const int r = half * 32 + lane;
+    bool hit = false;
+    if (r < k) {
+      const int id = ids[(size_t)q * k + r];
+      int lo = beg, hi = end;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (test_idx[mid] < id) lo = mid + 1;
+        else hi = mid;
+      }
+      hit = lo < end && test_idx[lo] == id;
+    }
+    mask |= (unsigned long long)__ballot_sync(SRB_FULL_MASK, hit) << (32 * half);
+  }
+  if (lane == 0) out[q] = mask;
+}
+}  // namespace srb
+
+extern "C" int srb_rank_hit_masks(const int32_t* topk_ids, int32_t n_q, int32_t k, const int32_t* users, const int32_t* test_ptr,
+                                  const int32_t* test_idx, uint64_t* hit_mask, void* stream) {
+  SRB_REQUIRE(n_q >= 0 && k >= 1 && k <= 64, "rank_hit_masks: k must be 1..64");
+  if (n_q == 0) return SRB_OK;
+  SRB_REQUIRE(topk_ids && users && test_ptr && test_idx && hit_mask, "rank_hit_masks: null pointer");
+  srb::rank_hit_masks_kernel<<<(n_q + 7) / 8, 256, 0, (cudaStream_t)stream>>>(topk_ids, n_q, k, users, test_ptr, test_idx,
+                                                                              reinterpret_cast<unsigned long long*>(hit_mask));
+  return srb::post_launch("rank_hit_masks_kernel");
+}

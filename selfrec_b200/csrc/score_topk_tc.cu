@@ -194,12 +194,17 @@ tc_score_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_const
     // candidate list: 32 (score, id) slots in shared memory (column `tix`), organised as 4 buckets of 8.
     // Registers keep each bucket's minimum and its slot, so replacing the global minimum re-scans only
     // one bucket (8 independent shared-memory loads) instead of the whole list.
+    // Each stored score carries its slot-in-bucket in the 3 low mantissa bits (the scores only rank candidates;
+    // the certificate in tc_rescore_kernel accounts for the 2^-20 relative perturbation), so a bucket's minimum
+    // names its own slot and 7 FMNMX replace a compare/select scan.
     float bm0 = INFINITY, bm1 = INFINITY, bm2 = INFINITY, bm3 = INFINITY;  // bucket minima (valid once full)
-    int bp0 = 0, bp1 = 8, bp2 = 16, bp3 = 24;                              // slot of each bucket's minimum
     auto process_group = [&](const uint32_t (&r)[32], int g0) {
       uint32_t mask = 0;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(r[j]) > thr) ? (1u << j) : 0u;
+      for (int j = 0; j < 32; ++j)  // two instructions per score: FSETP + predicated LOP3
+        asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}"
+            : "+r"(mask)
+            : "f"(__uint_as_float(r[j])), "f"(thr), "r"(1u << j));
       if (g0 + 32 > a.n_items) mask &= (g0 < a.n_items) ? (0xffffffffu >> (g0 + 32 - a.n_items)) : 0u;  // zero-filled OOB rows
       if (!active) mask = 0;
       // rated items never become candidates: walk the sorted rated list through this group
@@ -212,52 +217,55 @@ tc_score_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_const
       while (mask) {
         const int j = __ffs(mask) - 1;
         mask &= mask - 1;
-        float sc = 0.f;
+        // r[j] with a per-lane j: a 5-level select tree on the bits of j (31 selects)
+        uint32_t t16[16], t8[8], t4[4];
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj)
-          if (jj == j) sc = __uint_as_float(r[jj]);
+        for (int i = 0; i < 16; ++i) t16[i] = (j & 1) ? r[2 * i + 1] : r[2 * i];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t8[i] = (j & 2) ? t16[2 * i + 1] : t16[2 * i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) t4[i] = (j & 4) ? t8[2 * i + 1] : t8[2 * i];
+        const uint32_t t2a = (j & 8) ? t4[1] : t4[0], t2b = (j & 8) ? t4[3] : t4[2];
+        float sc = __uint_as_float((j & 16) ? t2b : t2a);
         if (!(sc > thr)) continue;  // thr may have risen inside this group
         const int id = g0 + j;
         if (cnt < TC_CAND) {
           cs[cnt * 256 + tix] = sc;
           ci[cnt * 256 + tix] = id;
           ++cnt;
-          if (cnt == TC_CAND) {  // list full: establish the bucket minima
+          if (cnt == TC_CAND) {  // list full: tag every slot and establish the bucket minima
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
               float mn = INFINITY;
-              int mp = b * 8;
 #pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const float v = cs[(b * 8 + q) * 256 + tix];
-                if (v < mn) mn = v, mp = b * 8 + q;
+              for (int qq = 0; qq < 8; ++qq) {
+                const float v = __uint_as_float((__float_as_uint(cs[(b * 8 + qq) * 256 + tix]) & ~7u) | (uint32_t)qq);
+                cs[(b * 8 + qq) * 256 + tix] = v;
+                mn = fminf(mn, v);
               }
-              if (b == 0) bm0 = mn, bp0 = mp;
-              if (b == 1) bm1 = mn, bp1 = mp;
-              if (b == 2) bm2 = mn, bp2 = mp;
-              if (b == 3) bm3 = mn, bp3 = mp;
+              if (b == 0) bm0 = mn;
+              if (b == 1) bm1 = mn;
+              if (b == 2) bm2 = mn;
+              if (b == 3) bm3 = mn;
             }
             thr = fminf(fminf(bm0, bm1), fminf(bm2, bm3));
           }
         } else {
-          // evict the global minimum: it sits in the bucket whose minimum equals thr
-          int b = 3, pos = bp3;
-          if (bm2 == thr) b = 2, pos = bp2;
-          if (bm1 == thr) b = 1, pos = bp1;
-          if (bm0 == thr) b = 0, pos = bp0;
-          cs[pos * 256 + tix] = sc;
+          // evict the global minimum: it sits in the bucket whose minimum equals thr, in the slot its tag names
+          int b = 3;
+          if (bm2 == thr) b = 2;
+          if (bm1 == thr) b = 1;
+          if (bm0 == thr) b = 0;
+          const int pos = b * 8 + (int)(__float_as_uint(thr) & 7u);
+          cs[pos * 256 + tix] = __uint_as_float((__float_as_uint(sc) & ~7u) | (__float_as_uint(thr) & 7u));
           ci[pos * 256 + tix] = id;
-          float mn = INFINITY;
-          int mp = b * 8;
+          float mn = cs[(b * 8) * 256 + tix];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float v = cs[(b * 8 + q) * 256 + tix];
-            if (v < mn) mn = v, mp = b * 8 + q;
-          }
-          if (b == 0) bm0 = mn, bp0 = mp;
-          if (b == 1) bm1 = mn, bp1 = mp;
-          if (b == 2) bm2 = mn, bp2 = mp;
-          if (b == 3) bm3 = mn, bp3 = mp;
+          for (int qq = 1; qq < 8; ++qq) mn = fminf(mn, cs[(b * 8 + qq) * 256 + tix]);
+          if (b == 0) bm0 = mn;
+          if (b == 1) bm1 = mn;
+          if (b == 2) bm2 = mn;
+          if (b == 3) bm3 = mn;
           thr = fminf(fminf(bm0, bm1), fminf(bm2, bm3));
         }
       }
@@ -370,7 +378,7 @@ __global__ void __launch_bounds__(256) tc_rescore_kernel(const RescoreArgs a) {
   // exactness test
   const float kth = __shfl_sync(SRB_FULL_MASK, ls, K - 1);
   const float bmax = __uint_as_float(*a.bmax_bits);
-  const float E = (1.0f / 512.0f + 1.0f / 65536.0f) * a.unorm[q] * bmax;
+  const float E = (1.0f / 512.0f + 1.0f / 65536.0f + 1.0f / 262144.0f) * a.unorm[q] * bmax;  // TF32 truncation + slot tags
   const float thr32 = a.cand_thr[q];
   int deg = 0;
   if (a.rated_ptr) {

@@ -1,5 +1,42 @@
 """Minimal mirror of data/loader.py (FileIO): `user item weight` triples per line."""
 import os
+from collections.abc import Sequence
+
+
+def _parse(file):
+    data = []
+    with open(file) as f:
+        for line in f:
+            parts = line.strip().split(" ")
+            data.append([parts[0], parts[1], float(parts[2])])
+    return data
+
+
+class TripleFile(Sequence):
+    """What FileIO.load_data_set returns: behaves like the reference's list of [user, item, weight] (parsed on
+    first use), and remembers its path so that Interaction can hand the file to the native builder
+    (csrc/dataset.cpp) instead of looping over a million Python lists."""
+
+    def __init__(self, path):
+        self.path = os.fspath(path)
+        self._rows = None
+
+    def _load(self):
+        if self._rows is None:
+            self._rows = _parse(self.path)
+        return self._rows
+
+    def __len__(self):
+        return len(self._load())
+
+    def __getitem__(self, k):
+        return self._load()[k]
+
+    def __iter__(self):
+        return iter(self._load())
+
+    def __eq__(self, other):
+        return list(self) == list(other)
 
 
 class FileIO(object):
@@ -18,9 +55,4 @@ class FileIO(object):
     def load_data_set(file, rec_type="graph"):
         if rec_type != "graph":
             raise NotImplementedError("selfrec_b200 covers the graph models only")
-        data = []
-        with open(file) as f:
-            for line in f:
-                parts = line.strip().split(" ")
-                data.append([parts[0], parts[1], float(parts[2])])
-        return data
+        return TripleFile(file)

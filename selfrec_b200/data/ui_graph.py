@@ -14,6 +14,13 @@ from .graph import Graph
 
 
 class Interaction(Data, Graph):
+    def __new__(cls, conf=None, training=None, test=None, *a, **kw):
+        # triples that still know their file (FileIO.load_data_set) go to the native builder
+        if cls is Interaction and getattr(training, "path", None) and (test is None or getattr(test, "path", None)):
+            from .native import NativeInteraction
+            return object.__new__(NativeInteraction)
+        return object.__new__(cls)
+
     def __init__(self, conf, training, test):
         Graph.__init__(self)
         Data.__init__(self, conf, training, test)
@@ -88,6 +95,24 @@ class Interaction(Data, Graph):
             m.sort_indices()
             self._rated = (m.indptr.astype(np.int32), m.indices.astype(np.int32))
         return self._rated
+
+    def test_csr(self):
+        """(ptr[int32 U+1], idx[int32], n_test[int32 U]): per user id the sorted unique ids of its test items
+        that have a training id, and len(test_set[user]) (which also counts items never seen in training)."""
+        if getattr(self, "_test_csr", None) is None:
+            U = len(self.user)
+            rows, n_test = [[] for _ in range(U)], np.zeros(U, dtype=np.int32)
+            for name, items in self.test_set.items():
+                uid = self.user.get(name)
+                if uid is None:
+                    continue
+                n_test[uid] = len(items)
+                rows[uid] = sorted({self.item[i] for i in items if i in self.item})
+            ptr = np.zeros(U + 1, dtype=np.int32)
+            ptr[1:] = np.cumsum([len(r) for r in rows])
+            idx = np.fromiter((i for r in rows for i in r), dtype=np.int32, count=int(ptr[-1]))
+            self._test_csr = (ptr, idx, n_test)
+        return self._test_csr
 
     def get_user_id(self, u):
         return self.user.get(u)

@@ -418,6 +418,24 @@ def adam_step(p, m, v, g, scalars, beta1=0.9, beta2=0.999, eps=1e-8):
     _lib.check(lib.srb_adam_step(_p(p), _p(m), _p(v), _p(g), p.numel(), _p(scalars), beta1, beta2, eps, _stream()), "srb_adam_step")
 
 
+def rank_hit_masks(topk_ids, users, test_ptr, test_idx):
+    """uint64 mask per query row: bit r set iff topk_ids[q, r] is a test item of users[q] (k <= 64).
+    topk_ids: device int32 [n_q, k]; users / test_ptr / test_idx: int32 arrays or tensors."""
+    lib = _lib.require_device()
+    dev = topk_ids.device
+    ids = topk_ids.contiguous()
+    if ids.dtype != torch.int32 or ids.dim() != 2:
+        raise TypeError("topk_ids must be an int32 [n_q, k] tensor")
+    to = lambda a: a.to(dev) if isinstance(a, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32)).to(dev)
+    users, test_ptr, test_idx = to(users), to(test_ptr), to(test_idx)
+    if test_idx.numel() == 0:
+        test_idx = torch.zeros(1, dtype=torch.int32, device=dev)
+    out = torch.zeros(ids.shape[0], dtype=torch.int64, device=dev)
+    _lib.check(lib.srb_rank_hit_masks(_p(ids), ids.shape[0], ids.shape[1], _p(users), _p(test_ptr), _p(test_idx), _p(out), _stream()),
+               "srb_rank_hit_masks")
+    return out
+
+
 def scatter_add_segments(dst, segs):
     """dst[rows + off] += scale * src for up to 8 (src, rows, n_dev, n, off, scale) segments, one launch."""
     lib = _lib.require_device()

@@ -470,3 +470,37 @@ def test_graph_recommender_test_and_fast_evaluation(torch_cuda, golden, tiny, ti
     assert m.bestPerformance[0] == 1 and hasattr(m, "best_user_emb")
     sc = m.predict(r["users"][0])
     assert sc.shape == (tiny["I"],) and sc.dtype == np.float32
+
+
+def test_rank_hit_masks_and_fast_measure(torch_cuda, golden, tiny_triples, tiny_conf, in_tmp_cwd):
+    """srb_rank_hit_masks against a numpy restatement on random lists, and the id-space fast_evaluation path
+    against ranking_evaluation over the name-keyed test() output (the reference's route)."""
+    torch = torch_cuda
+    from selfrec_b200 import ops
+    from selfrec_b200.util.evaluation import ranking_evaluation, ranking_evaluation_from_masks
+    rng = np.random.default_rng(5)
+    U, I, K = 300, 1000, 20
+    ptr = np.zeros(U + 1, dtype=np.int32)
+    rows = [np.sort(rng.choice(I, size=rng.integers(0, 30), replace=False)).astype(np.int32) for _ in range(U)]
+    ptr[1:] = np.cumsum([len(x) for x in rows])
+    idx = np.concatenate(rows).astype(np.int32)
+    users = rng.permutation(U)[:257].astype(np.int32)
+    ids = np.stack([rng.choice(I, size=K, replace=False) for _ in users]).astype(np.int32)
+    got = ops.rank_hit_masks(torch.from_numpy(ids).cuda(), users, ptr, idx).cpu().numpy().view(np.uint64)
+    want = np.array([sum(1 << r for r in range(K) if ids[q, r] in set(rows[u].tolist())) for q, u in enumerate(users)], dtype=np.uint64)
+    assert (got == want).all()
+    for k in (1, 33, 64):
+        ids2 = np.stack([rng.choice(I, size=k, replace=False) for _ in users]).astype(np.int32)
+        g2 = ops.rank_hit_masks(torch.from_numpy(ids2).cuda(), users, ptr, idx).cpu().numpy().view(np.uint64)
+        w2 = np.array([sum(1 << r for r in range(k) if ids2[q, r] in set(rows[u].tolist())) for q, u in enumerate(users)], dtype=np.uint64)
+        assert (g2 == w2).all()
+    # whole fast path on the golden embeddings
+    from selfrec_b200.base.graph_recommender import GraphRecommender
+    train, test = tiny_triples
+    r = golden("rank.npz")
+    m = GraphRecommender(tiny_conf("MF"), [list(t) for t in train], [list(t) for t in test])
+    m.user_emb = torch.from_numpy(r["user_emb"]).cuda()
+    m.item_emb = torch.from_numpy(r["item_emb"]).cuda()
+    fast = m._fast_measure()
+    slow = ranking_evaluation(m.data.test_set, m.test(), [m.max_N])
+    assert fast == slow

@@ -8,6 +8,8 @@ import numpy as np
 import pytest
 import scipy.sparse as sp
 
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -187,6 +189,100 @@ def test_ranking_evaluation_format(golden, tiny_triples, tiny_conf, in_tmp_cwd):
     d = Interaction(tiny_conf("MF"), [list(t) for t in train], [list(t) for t in test])
     rec = {u: list(zip(r["items"][k], r["scores"][k].tolist())) for k, u in enumerate(r["users"])}
     assert ranking_evaluation(d.test_set, rec, [5, 10]) == list(r["measure"])
+
+
+def test_ranking_evaluation_from_masks_matches_reference_strings(golden, tiny_triples, tiny_conf, in_tmp_cwd):
+    """The id-space metric path (hit masks -> reference float expressions) reproduces the reference's
+    ranking_evaluation() output on the golden full test() run, string for string."""
+    from selfrec_b200.data.ui_graph import Interaction
+    from selfrec_b200.util.evaluation import ranking_evaluation_from_masks
+    train, test = tiny_triples
+    r = golden("rank.npz")
+    d = Interaction(tiny_conf("MF"), [list(t) for t in train], [list(t) for t in test])
+    test_ptr, test_idx, n_test = d.test_csr()
+    uids = np.array([d.user[u] for u in r["users"]], dtype=np.int32)
+    assert list(r["users"]) == list(d.test_set)
+    masks = []
+    for k, u in enumerate(uids):
+        mine = set(test_idx[test_ptr[u]:test_ptr[u + 1]].tolist())
+        masks.append(sum(1 << rk for rk, name in enumerate(r["items"][k]) if d.item[name] in mine))
+    for u, name in zip(uids, r["users"]):
+        assert n_test[u] == len(d.test_set[name])
+    assert ranking_evaluation_from_masks(n_test[uids], masks, [5, 10]) == list(r["measure"])
+
+
+def _same_csr(x, y):
+    x, y = x.tocsr().copy(), y.tocsr().copy()
+    x.sort_indices()
+    y.sort_indices()
+    return (x.shape == y.shape and (x.indptr == y.indptr).all() and (x.indices == y.indices).all()
+            and (x.data.view(np.uint32) == y.data.view(np.uint32)).all())
+
+
+def _assert_same_interaction(a, b):
+    assert a.user == b.user and a.item == b.item and a.id2user == b.id2user and a.id2item == b.id2item
+    assert (a.pair_users == b.pair_users).all() and (a.pair_items == b.pair_items).all()
+    assert _same_csr(a.norm_adj, b.norm_adj) and _same_csr(a.ui_adj, b.ui_adj) and _same_csr(a.interaction_mat, b.interaction_mat)
+    assert dict(a.test_set) == dict(b.test_set) and list(a.test_set) == list(b.test_set) and a.test_set_item == b.test_set_item
+    assert a.training_size() == b.training_size() and a.test_size() == b.test_size()
+    assert a.training_data == b.training_data
+    assert dict(a.training_set_u) == dict(b.training_set_u) and dict(a.training_set_i) == dict(b.training_set_i)
+    for x, y in zip(a.rated_csr(), b.rated_csr()):
+        assert (x == y).all()
+
+
+def test_native_dataset_builder_matches_python_interaction(built_lib, golden, tmp_path):
+    """srb_dataset_* (C++) against the Python restatement of loader + Interaction (itself pinned to the
+    reference by graph.npz): ids, pairs, all three matrices bit for bit, test filtering, sizes."""
+    from selfrec_b200.data.loader import FileIO
+    from selfrec_b200.data.native import load_interaction
+    from selfrec_b200.data.ui_graph import Interaction
+    tr, te = os.path.join(GOLDEN, "tiny_train.txt"), os.path.join(GOLDEN, "tiny_test.txt")
+    a = load_interaction(None, tr, te)
+    py = Interaction(None, list(FileIO.load_data_set(tr)), list(FileIO.load_data_set(te)))  # plain lists: the Python route
+    assert type(py) is Interaction and type(a) is not Interaction
+    _assert_same_interaction(a, py)
+    g = golden("graph.npz")  # the reference's own matrices
+    ref = sp.csr_matrix((g["norm_data"], g["norm_indices"], g["norm_indptr"]), shape=a.norm_adj.shape)
+    assert _same_csr(a.norm_adj, ref)
+    # a harder file: duplicates, hubs, users/items unseen in training, trailing blanks, \r\n, no final newline
+    rng = np.random.default_rng(3)
+    n_u, n_i = 400, 300
+    lines = [f"user{rng.integers(n_u)} it{int(rng.zipf(1.3)) % n_i} {rng.integers(1, 6)}" for _ in range(20000)]
+    lines[5] += "   "
+    lines[7] = "  " + lines[7] + "\r"
+    lines[11] += " extra column"
+    tr2, te2 = tmp_path / "train.txt", tmp_path / "test.txt"
+    tr2.write_text("\n".join(lines))
+    tl = [f"user{rng.integers(n_u + 50)} it{rng.integers(n_i + 80)} 1.5" for _ in range(3000)]
+    te2.write_text("\n".join(tl) + "\n")
+    a2 = load_interaction(None, tr2, te2)
+    _assert_same_interaction(a2, Interaction(None, list(FileIO.load_data_set(str(tr2))), list(FileIO.load_data_set(str(te2)))))
+    # FileIO's return value keeps its path, so the reference's own call sequence lands in the native builder
+    via_fileio = Interaction(None, FileIO.load_data_set(str(tr2)), FileIO.load_data_set(str(te2)))
+    assert type(via_fileio) is not Interaction
+    _assert_same_interaction(via_fileio, a2)
+    assert a2.ui_adj.data.max() > 1.0  # duplicate lines were summed
+    # no test file
+    a3 = load_interaction(None, tr2)
+    assert len(a3.test_set) == 0 and a3.test_size() == (0, 0, 0) and _same_csr(a3.norm_adj, a2.norm_adj)
+
+
+def test_native_dataset_builder_errors(built_lib, tmp_path):
+    from selfrec_b200 import _lib
+    from selfrec_b200.data.native import load_interaction
+    with pytest.raises(_lib.SrbError, match="cannot open"):
+        load_interaction(None, tmp_path / "missing.txt")
+    bad = tmp_path / "bad.txt"
+    bad.write_text("u1 i1 1\nu2 i2\n")
+    with pytest.raises(_lib.SrbError, match="line 2"):
+        load_interaction(None, bad)
+    bad.write_text("u1 i1 abc\n")
+    with pytest.raises(_lib.SrbError, match="line 1"):
+        load_interaction(None, bad)
+    bad.write_text("u1 i1 1\n\nu2 i2 1\n")  # the reference dies on an empty line (IndexError)
+    with pytest.raises(_lib.SrbError, match="line 2"):
+        load_interaction(None, bad)
 
 
 def test_install_aliases_boundary_modules(built_lib):
