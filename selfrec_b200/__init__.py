@@ -18,6 +18,9 @@ _DROPIN = {
     "util.loss_torch": "selfrec_b200.util.loss_torch",
     "util.sampler": "selfrec_b200.util.sampler",
     "data.ui_graph": "selfrec_b200.data.ui_graph",
+    # file -> CSR through the native builder, ranking metrics from device hit masks
+    "data.loader": "selfrec_b200.data.loader",
+    "util.evaluation": "selfrec_b200.util.evaluation",
 }
 _FUSED_MODELS = {f"model.graph.{m}": f"selfrec_b200.model.graph.{m}" for m in ("MF", "LightGCN", "SimGCL", "XSimGCL", "SGL")}
 

@@ -250,35 +250,38 @@ template <int D>
 __global__ void __launch_bounds__(256) fb_score_kernel(const float* __restrict__ user_emb, const float* __restrict__ item_emb,
                                                       const int32_t* __restrict__ fb_users, const int32_t* __restrict__ fb_count,
                                                       const int32_t* __restrict__ rated_ptr, const int32_t* __restrict__ rated_idx,
-                                                      int n_items, float* __restrict__ scratch) {
-  const int slot = blockIdx.y;
-  if (slot >= *fb_count) return;
+                                                      int n_items, float* __restrict__ scratch, int cap) {
+  // the usual case is zero fallback users: a small grid.y that strides over the slots keeps that case cheap
+  const int count = min(*fb_count, cap);
   __shared__ float us[D];
-  const int u = fb_users[slot];
-  for (int k = threadIdx.x; k < D; k += blockDim.x) us[k] = user_emb[(size_t)u * D + k];
-  __syncthreads();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_items) return;
-  const float* it = item_emb + (size_t)i * D;
-  float acc = 0.f;
+  for (int slot = blockIdx.y; slot < count; slot += gridDim.y) {
+    const int u = fb_users[slot];
+    __syncthreads();
+    for (int k = threadIdx.x; k < D; k += blockDim.x) us[k] = user_emb[(size_t)u * D + k];
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_items) continue;
+    const float* it = item_emb + (size_t)i * D;
+    float acc = 0.f;
 #pragma unroll 8
-  for (int k4 = 0; k4 < D / 4; ++k4) {
-    const float4 v = ldg4(it + k4 * 4);
-    acc = fmaf(us[k4 * 4 + 0], v.x, acc);
-    acc = fmaf(us[k4 * 4 + 1], v.y, acc);
-    acc = fmaf(us[k4 * 4 + 2], v.z, acc);
-    acc = fmaf(us[k4 * 4 + 3], v.w, acc);
-  }
-  if (rated_ptr) {  // binary search of item i in the user's sorted rated list
-    int lo = rated_ptr[u], hi = rated_ptr[u + 1];
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      const int v = rated_idx[mid];
-      if (v < i) lo = mid + 1; else hi = mid;
+    for (int k4 = 0; k4 < D / 4; ++k4) {
+      const float4 v = ldg4(it + k4 * 4);
+      acc = fmaf(us[k4 * 4 + 0], v.x, acc);
+      acc = fmaf(us[k4 * 4 + 1], v.y, acc);
+      acc = fmaf(us[k4 * 4 + 2], v.z, acc);
+      acc = fmaf(us[k4 * 4 + 3], v.w, acc);
     }
-    if (lo < rated_ptr[u + 1] && rated_idx[lo] == i) acc = TK_MASKED;
+    if (rated_ptr) {  // binary search of item i in the user's sorted rated list
+      int lo = rated_ptr[u], hi = rated_ptr[u + 1];
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const int v = rated_idx[mid];
+        if (v < i) lo = mid + 1; else hi = mid;
+      }
+      if (lo < rated_ptr[u + 1] && rated_idx[lo] == i) acc = TK_MASKED;
+    }
+    scratch[(size_t)slot * n_items + i] = acc;
   }
-  scratch[(size_t)slot * n_items + i] = acc;
 }
 
 __global__ void __launch_bounds__(256) fb_topk_kernel(const float* scratch, const int32_t* fb_rows, const int32_t* fb_count, int cap,
@@ -319,9 +322,9 @@ __global__ void __launch_bounds__(256) fb_topk_kernel(const float* scratch, cons
 int score_topk_fallback(const srb_topk_desc* d, const int32_t* fb_users, const int32_t* fb_rows, const int32_t* fb_count,
                         float* scratch, int fb_cap, cudaStream_t st) {
   // fast path: up to fb_cap users
-  dim3 grid((d->n_items + 255) / 256, fb_cap);
+  dim3 grid((d->n_items + 255) / 256, fb_cap < 8 ? fb_cap : 8);
   fb_score_kernel<64><<<grid, 256, 0, st>>>(d->user_emb, d->item_emb, fb_users, fb_count, d->rated_ptr, d->rated_idx, d->n_items,
-                                            scratch);
+                                            scratch, fb_cap);
   SRB_TRY(post_launch("fb_score_kernel"));
   fb_topk_kernel<<<(fb_cap + 7) / 8, 256, 0, st>>>(scratch, fb_rows, fb_count, fb_cap, d->n_items, d->k, d->out_ids, d->out_scores);
   SRB_TRY(post_launch("fb_topk_kernel"));

@@ -40,10 +40,13 @@ class TripleFile(Sequence):
 
 
 class FileIO(object):
+    """data/loader.py's FileIO.  The graph format goes through TripleFile (and from there to the native builder);
+    the other readers are plain restatements so that aliasing this module never takes a format away."""
+
     @staticmethod
     def write_file(dir, file, content, op="w"):
         os.makedirs(dir, exist_ok=True)
-        with open(os.path.join(dir, file), op) as f:
+        with open(dir + file, op) as f:  # plain concatenation, as the reference does (loader.py:14)
             f.writelines(content)
 
     @staticmethod
@@ -53,6 +56,25 @@ class FileIO(object):
 
     @staticmethod
     def load_data_set(file, rec_type="graph"):
-        if rec_type != "graph":
-            raise NotImplementedError("selfrec_b200 covers the graph models only")
-        return TripleFile(file)
+        if rec_type == "graph":
+            return TripleFile(file)
+        if rec_type == "sequential":  # `seq_id:item item ...` per line (loader.py:34-40); not on the hot path
+            with open(file) as f:
+                return {head: tail.split() for head, tail in (line.strip().split(":")[:2] for line in f)}
+        raise ValueError(f"unknown dataset type {rec_type!r}")
+
+    @staticmethod
+    def load_user_list(file):
+        print("loading user List...")
+        with open(file) as f:
+            return [line.strip().split()[0] for line in f]
+
+    @staticmethod
+    def load_social_data(file):
+        print("loading social data...")
+        out = []
+        with open(file) as f:
+            for line in f:
+                parts = line.strip().split(" ")
+                out.append([parts[0], parts[1], 1 if len(parts) < 3 else float(parts[2])])
+        return out
