@@ -5,6 +5,7 @@
 The shared library has no torch dependency: plain `extern "C"` entry points declared in
 include/selfrec_b200.h.  It is git-ignored but travels to the GPU box with the snapshot.
 """
+import fcntl
 import hashlib
 import os
 import shutil
@@ -16,7 +17,8 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(ROOT, "include")
 LIB = os.path.join(HERE, "libselfrec_b200.so")
-STAMP = os.path.join(HERE, ".libselfrec_b200.stamp")
+STAMP = os.path.join(HERE, "libselfrec_b200.stamp")  # no leading dot: it has to travel with the .so
+LOCK = os.path.join(HERE, "libselfrec_b200.lock")
 
 SOURCES = ["capi.cu", "spmm.cu", "bpr.cu", "infonce.cu", "score_topk.cu", "score_topk_tc.cu", "engine.cu", "sampler.cpp", "dataset.cpp"]
 NVCC_FLAGS = [
@@ -56,6 +58,18 @@ def build(force=False, verbose=False):
     """Compile every CUDA source for sm_100a into selfrec_b200/libselfrec_b200.so."""
     if not force and not needs_build():
         return LIB
+    # several ranks of one job may get here at once: one builds, the others wait and find it done
+    with open(LOCK, "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():
+                return LIB
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose):
     objs = []
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
@@ -79,12 +93,15 @@ def build(force=False, verbose=False):
             sys.stderr.write(f"[selfrec_b200.build] {src}:\n{out}\n")
     if failed:
         raise RuntimeError("nvcc failed; see messages above")
-    link = [nvcc, "--shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
+    tmp = LIB + f".tmp{os.getpid()}"
+    link = [nvcc, "--shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp] + objs
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout)
-    with open(STAMP, "w") as fh:
+    os.replace(tmp, LIB)  # a process that already mapped the old library keeps its inode
+    with open(STAMP + ".tmp", "w") as fh:
         fh.write(_digest())
+    os.replace(STAMP + ".tmp", STAMP)
     return LIB
 
 
