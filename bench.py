@@ -364,6 +364,11 @@ def run_ours(args, rank, world, local_rank):
         "roofline": {"bound": "hbm", "kernel": "spmm_csr_kernel<64>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "ms_per_launch": spmm_ms,
                      "algorithmic_bytes_per_launch": alg,
+                     # what actually bounds this kernel: the X rows are L2-resident and every non-zero gathers one
+                     # 256-byte row out of L2; ceiling measured by tools/l2_microbench.cu (profiles/r01a_l2_gather_microbench.txt)
+                     "l2_gather": {"bytes_per_launch": 4 * nnzA * CFG["d"], "achieved": 4 * nnzA * CFG["d"] / (spmm_ms * 1e-3) / 1e9,
+                                   "peak": 18500.0, "unit": "GB/s", "frac": 4 * nnzA * CFG["d"] / (spmm_ms * 1e-3) / 1e9 / 18500.0,
+                                   "peak_source": "measured random 256 B row gathers from an L2-resident table, 148 SMs"},
                      "step": {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (ms / args.steps * 1e-3) / 1e9,
                               "frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak}},
         "rank": {"metric": "full-catalog rank items/sec", "value": rank_val, "unit": "items/s", "ms": rank_ms,

@@ -504,3 +504,72 @@ def test_rank_hit_masks_and_fast_measure(torch_cuda, golden, tiny_triples, tiny_
     fast = m._fast_measure()
     slow = ranking_evaluation(m.data.test_set, m.test(), [m.max_N])
     assert fast == slow
+
+
+class _SynthData:
+    """What TrainEngine reads from an Interaction, for a random bipartite graph."""
+
+    def __init__(self, rng, U, I, n_pairs):
+        import scipy.sparse as sp_
+        pu = rng.integers(0, U, n_pairs).astype(np.int32)
+        pi = (rng.zipf(1.5, n_pairs) % I).astype(np.int32)
+        pu[:U] = np.arange(U)  # every user and item appears
+        pi[:I] = np.arange(I)
+        self.user_num, self.item_num = U, I
+        self.pair_users, self.pair_items = pu, pi
+        n = U + I
+        half = sp_.csr_matrix((np.ones(n_pairs, np.float32), (pu, pi.astype(np.int64) + U)), shape=(n, n), dtype=np.float32)
+        adj = half + half.T
+        d = np.asarray(adj.sum(1)).ravel()
+        dinv = np.where(d > 0, d ** -0.5, 0).astype(np.float32)
+        self.norm_adj = sp_.diags(dinv).dot(adj).dot(sp_.diags(dinv)).tocsr().astype(np.float32)
+        self.training_data = []
+
+
+@pytest.mark.parametrize("name,d,L,lcl", [("XSimGCL", 32, 2, 1), ("XSimGCL", 128, 3, 3), ("XSimGCL", 64, 1, 1), ("XSimGCL", 64, 2, 0),
+                                          ("SimGCL", 128, 2, 0), ("LightGCN", 32, 3, 0), ("MF", 128, 0, 0)])
+def test_engine_steps_vs_oracle_other_widths_and_partial_batches(torch_cuda, orc, name, d, L, lcl):
+    """The fused step against the float64 oracle at embedding sizes 32 / 128 (CUDA-core InfoNCE, other SpMM
+    instantiations), with every position of the contrastive layer, a short last batch and an EMPTY batch
+    (which must leave parameters to Adam's zero-gradient update, exactly like the oracle)."""
+    torch = torch_cuda
+    from selfrec_b200.engine import TrainEngine
+    rng = np.random.default_rng(d * 10 + L)
+    U, I, B = 150, 220, 64
+    data = _SynthData(rng, U, I, 3000)
+    N = U + I
+    E0 = (rng.standard_normal((N, d)) * 0.1).astype(np.float32)
+    kw = dict(eps=0.2, tau=0.2, cl_rate=0.3, layer_cl=lcl) if name in ("XSimGCL", "SimGCL") else {}
+    if name in ("MF", "LightGCN"):
+        kw["l2_div"] = float(B)
+    eng = TrainEngine(name, data, d, L, B, 1e-2, 1e-3, init_user=torch.from_numpy(E0[:U]), init_item=torch.from_numpy(E0[U:]), **kw)
+    views = 2 if name == "SimGCL" else 1
+    p, m, v = E0.copy(), np.zeros_like(E0), np.zeros_like(E0)
+    for step, b in enumerate((B, 17, 0, B), start=1):
+        u = rng.integers(0, U, b).astype(np.int32)
+        i = rng.integers(0, I, b).astype(np.int32)
+        j = rng.integers(0, I, b).astype(np.int32)
+        noise = None
+        if name in ("XSimGCL", "SimGCL"):
+            noise = rng.random((views, max(L, 1), N, d), dtype=np.float32)
+            eng.set_noise_tensor(torch.from_numpy(noise[:, :L]).cuda())
+        eng.step(_batch_words(u, i, j, B))
+        torch.cuda.synchronize()
+        if b == 0:
+            g, ref = np.zeros((N, d)), None
+        else:
+            ref = orc.train_step(name, data.norm_adj if name != "MF" else None, p, U, u, i, j, n_layers=L, reg=1e-3,
+                                 batch_size=B, eps=0.2, tau=0.2, cl_rate=0.3, layer_cl=lcl, noise=None if noise is None else noise[:, :L])
+            g = ref["grad"]
+        p, m, v = orc.adam_step(p, g.astype(np.float32), m, v, step, 1e-2)
+        got = eng.params.cpu().numpy()
+        # Adam divides by sqrt(v) + 1e-8: entries whose gradient is ~1e-8 or below are ill-conditioned in fp32
+        cond = np.abs(g) > 1e-6
+        np.testing.assert_allclose(got[cond], p[cond], rtol=RTOL, atol=2e-6, err_msg=f"{name} d={d} step {step} b={b}")
+        assert np.abs(got - p).max() <= 2.5e-2  # lr-bounded everywhere (|update| <= lr / (1 - beta1) early on)
+        if ref is not None:
+            los = eng.losses.cpu().numpy()
+            assert abs(los[0] - ref["rec"]) <= RTOL * abs(ref["rec"]) + 1e-7
+            assert abs(los[2] - ref["cl"]) <= RTOL * abs(ref["cl"]) + 2e-7 / 0.2
+        p = got.astype(np.float32).copy()  # continue from the device state: errors do not compound across steps
+        m, v = eng.m.cpu().numpy().copy(), eng.v.cpu().numpy().copy()
