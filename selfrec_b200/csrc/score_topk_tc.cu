@@ -12,16 +12,17 @@
 //            warp 1   MMA issuer : tcgen05.mma kind::tf32, M=128 (users) x N=128 (items) x K=8,
 //                                  2 user halves x 8 k-steps per tile, accumulators in TMEM
 //                                  (2 stages x 2 halves x 128 columns = all 512 columns)
-//            warps 2-9 epilogue  : tcgen05.ld (lane = user row, next group's load in flight while one
-//                                  is processed), rated-item cursor, per-thread top-32 candidate
-//                                  list (4 buckets of 8, minima in registers) in shared memory
+//            warps 2-17 epilogue : 16 warps (4 per scheduler: the select loop is latency-bound), thread =
+//                                  one user row x one 64-column half of the tile: tcgen05.ld (lane = user
+//                                  row), rated-item cursor, per-thread top-24 candidate list (3 buckets
+//                                  of 8, minima in registers) in shared memory -> 2 x 24 candidates per user
 //          The raw fp32 tables are fed to the tensor core, which reads them as TF32 (low 13
 //          mantissa bits ignored): scores carry <= 2^-9 ||u|| ||i|| error -- candidates only.
-// Stage 3  tc_rescore_kernel    warp per user: exact fp32 fma-chain scores of the 32 candidates
+// Stage 3  tc_rescore_kernel    warp per user: exact fp32 fma-chain scores of the 2 x 24 candidates
 //                               (bit-identical to impl 1 / the oracle), find_k_largest's sequential
-//                               insertion in id order, and a safety test: every non-candidate has
-//                               approx score <= thr32, so the result is exact iff
-//                               thr32 + E < exact k-th score.  Users failing it (or with fewer than
+//                               insertion in id order, and a safety test: every non-candidate of a column
+//                               half has approx score <= that half's 24th best, so the result is exact iff
+//                               thr32 := max of the two + E < exact k-th score.  Users failing it (or with fewer than
 //                               k unrated items) are re-run by the exact CUDA-core kernel (impl 1).
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -32,23 +33,25 @@ using namespace tc;
 
 constexpr int TC_D = 64;          // embedding size handled by this kernel
 constexpr int TC_TN = 128;        // items per tile (UMMA N)
-constexpr int TC_STAGES = 3;      // smem ring depth
-constexpr int TC_CAND = 32;       // candidates kept per user
-constexpr int TC_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int TC_STAGES = 2;      // smem ring depth (a tile's select takes ~2 us: one tile of prefetch is enough)
+constexpr int TC_LIST = 24;       // candidates per list; every user has two lists, one per column half of the tiles
+constexpr int TC_CAND = 2 * TC_LIST;
+constexpr int TC_EPI_WARPS = 16;
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;   // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue
 constexpr uint32_t TC_TILE_BYTES = TC_TN * TC_D * 4;     // 32 KB: 2 k-chunks x [128][32] fp32
 constexpr uint32_t TC_USER_BYTES = 2 * 128 * TC_D * 4;   // 64 KB: 2 halves x 2 k-chunks x [128][32]
 
 struct TcSmem {
   // dynamic shared memory, 1024-byte aligned base:
   //   [0, 64K)          user tiles   half h, chunk c at (h*2 + c) * 16 KB
-  //   [64K, 64K+96K)    item stages  stage s, chunk c at 64K + s*32K + c*16K
-  //   then candidate lists: scores [32][256] f32, ids [32][256] i32   (64 KB)
+  //   [64K, 64K+64K)    item stages  stage s, chunk c at 64K + s*32K + c*16K
+  //   then candidate lists: scores [24][512] f32, ids [24][512] i32   (96 KB)
   //   then barriers
   static constexpr uint32_t users_off = 0;
   static constexpr uint32_t items_off = TC_USER_BYTES;
   static constexpr uint32_t cand_s_off = items_off + TC_STAGES * TC_TILE_BYTES;
-  static constexpr uint32_t cand_i_off = cand_s_off + TC_CAND * 256 * 4;
-  static constexpr uint32_t bar_off = cand_i_off + TC_CAND * 256 * 4;
+  static constexpr uint32_t cand_i_off = cand_s_off + TC_LIST * 512 * 4;
+  static constexpr uint32_t bar_off = cand_i_off + TC_LIST * 512 * 4;
   static constexpr uint32_t total = bar_off + 256;
 };
 
@@ -59,10 +62,10 @@ struct TcArgs {
   int32_t n_q;
   int32_t n_items;
   int32_t ub;                // users per CTA (<= 256)
-  float* cand_s;             // [n_q][32] approx scores
-  int32_t* cand_i;           // [n_q][32]
-  int32_t* cand_n;           // [n_q]
-  float* cand_thr;           // [n_q] min approx score of a full list, else -inf
+  float* cand_s;             // [n_q][2][24] approx scores
+  int32_t* cand_i;           // [n_q][2][24]
+  int32_t* cand_n;           // [n_q][2]
+  float* cand_thr;           // [n_q][2] min approx score of a full list, else -inf
 };
 
 __global__ void __launch_bounds__(256) tc_gather_kernel(const float* __restrict__ user_emb, const int32_t* __restrict__ users, int n_q,
@@ -81,7 +84,9 @@ __global__ void __launch_bounds__(256) tc_gather_kernel(const float* __restrict_
     const int i = w - n_q_pad;
     const float2 v = *reinterpret_cast<const float2*>(item_emb + (size_t)i * TC_D + lane * 2);
     const float ss = warp_sum(v.x * v.x + v.y * v.y);
-    if (lane == 0) atomicMax(bmax_bits, __float_as_uint(sqrtf(ss)));  // non-negative floats order like uints
+    // non-negative floats order like uints; 38 k atomics on one word serialise, so look before touching it
+    const unsigned int bits = __float_as_uint(sqrtf(ss));
+    if (lane == 0 && bits > *reinterpret_cast<volatile unsigned int*>(bmax_bits)) atomicMax(bmax_bits, bits);
   }
 }
 
@@ -108,7 +113,7 @@ tc_score_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_const
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_tfull + s, 1);
-      mbar_init(bar_tempty + s, 8);  // one arrive per epilogue warp
+      mbar_init(bar_tempty + s, TC_EPI_WARPS);  // one arrive per epilogue warp
     }
     mbar_init(bar_users, 1);
     fence_barrier_init();
@@ -169,14 +174,15 @@ tc_score_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_const
       }
     }
   } else {
-    // ===== epilogue: 8 warps, thread = one user row =====
+    // ===== epilogue: 16 warps, thread = one user row x one 64-column half of every tile =====
     const int e = warp - 2;
-    const int half = e >> 2;
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int half = (e >> 2) & 1;  // user half (accumulator)
+    const int chalf = e >> 3;       // column half
+    const int quarter = warp & 3;   // TMEM lane quarter this warp may access
     const int row = half * 128 + quarter * 32 + lane;
     const int q = q0 + row;
     const bool active = row < a.ub && q < a.n_q;
-    const int tix = row;  // column in the candidate arrays
+    const int tix = chalf * 256 + row;  // column in the candidate arrays
     float* cs = reinterpret_cast<float*>(sm + TcSmem::cand_s_off);
     int32_t* ci = reinterpret_cast<int32_t*>(sm + TcSmem::cand_i_off);
     float thr = -INFINITY;
@@ -191,13 +197,13 @@ tc_score_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_const
       if (cur < cend) next_rated = a.rated_idx[cur];
       if (cur + 1 < cend) after_next = a.rated_idx[cur + 1];
     }
-    // candidate list: 32 (score, id) slots in shared memory (column `tix`), organised as 4 buckets of 8.
-    // Registers keep each bucket's minimum and its slot, so replacing the global minimum re-scans only
-    // one bucket (8 independent shared-memory loads) instead of the whole list.
+    // candidate list: 24 (score, id) slots in shared memory (column `tix`), organised as 3 buckets of 8.
+    // Registers keep each bucket's minimum, so replacing the global minimum re-scans only one bucket
+    // (8 independent shared-memory loads) instead of the whole list.
     // Each stored score carries its slot-in-bucket in the 3 low mantissa bits (the scores only rank candidates;
     // the certificate in tc_rescore_kernel accounts for the 2^-20 relative perturbation), so a bucket's minimum
     // names its own slot and 7 FMNMX replace a compare/select scan.
-    float bm0 = INFINITY, bm1 = INFINITY, bm2 = INFINITY, bm3 = INFINITY;  // bucket minima (valid once full)
+    float bm0 = INFINITY, bm1 = INFINITY, bm2 = INFINITY;  // bucket minima (valid once full)
     auto process_group = [&](const uint32_t (&r)[32], int g0) {
       uint32_t mask = 0;
 #pragma unroll
@@ -229,44 +235,39 @@ tc_score_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_const
         float sc = __uint_as_float((j & 16) ? t2b : t2a);
         if (!(sc > thr)) continue;  // thr may have risen inside this group
         const int id = g0 + j;
-        if (cnt < TC_CAND) {
-          cs[cnt * 256 + tix] = sc;
-          ci[cnt * 256 + tix] = id;
+        if (cnt < TC_LIST) {
+          cs[cnt * 512 + tix] = sc;
+          ci[cnt * 512 + tix] = id;
           ++cnt;
-          if (cnt == TC_CAND) {  // list full: tag every slot and establish the bucket minima
+          if (cnt == TC_LIST) {  // list full: tag every slot and establish the bucket minima
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
+            for (int b = 0; b < 3; ++b) {
               float mn = INFINITY;
 #pragma unroll
               for (int qq = 0; qq < 8; ++qq) {
-                const float v = __uint_as_float((__float_as_uint(cs[(b * 8 + qq) * 256 + tix]) & ~7u) | (uint32_t)qq);
-                cs[(b * 8 + qq) * 256 + tix] = v;
+                const float v = __uint_as_float((__float_as_uint(cs[(b * 8 + qq) * 512 + tix]) & ~7u) | (uint32_t)qq);
+                cs[(b * 8 + qq) * 512 + tix] = v;
                 mn = fminf(mn, v);
               }
               if (b == 0) bm0 = mn;
               if (b == 1) bm1 = mn;
               if (b == 2) bm2 = mn;
-              if (b == 3) bm3 = mn;
             }
-            thr = fminf(fminf(bm0, bm1), fminf(bm2, bm3));
+            thr = fminf(fminf(bm0, bm1), bm2);
           }
         } else {
           // evict the global minimum: it sits in the bucket whose minimum equals thr, in the slot its tag names
-          int b = 3;
-          if (bm2 == thr) b = 2;
-          if (bm1 == thr) b = 1;
-          if (bm0 == thr) b = 0;
+          const int b = (bm0 == thr) ? 0 : ((bm1 == thr) ? 1 : 2);
           const int pos = b * 8 + (int)(__float_as_uint(thr) & 7u);
-          cs[pos * 256 + tix] = __uint_as_float((__float_as_uint(sc) & ~7u) | (__float_as_uint(thr) & 7u));
-          ci[pos * 256 + tix] = id;
-          float mn = cs[(b * 8) * 256 + tix];
+          cs[pos * 512 + tix] = __uint_as_float((__float_as_uint(sc) & ~7u) | (__float_as_uint(thr) & 7u));
+          ci[pos * 512 + tix] = id;
+          float mn = cs[(b * 8) * 512 + tix];
 #pragma unroll
-          for (int qq = 1; qq < 8; ++qq) mn = fminf(mn, cs[(b * 8 + qq) * 256 + tix]);
+          for (int qq = 1; qq < 8; ++qq) mn = fminf(mn, cs[(b * 8 + qq) * 512 + tix]);
           if (b == 0) bm0 = mn;
-          if (b == 1) bm1 = mn;
-          if (b == 2) bm2 = mn;
-          if (b == 3) bm3 = mn;
-          thr = fminf(fminf(bm0, bm1), fminf(bm2, bm3));
+          else if (b == 1) bm1 = mn;
+          else bm2 = mn;
+          thr = fminf(fminf(bm0, bm1), bm2);
         }
       }
     };
@@ -275,32 +276,28 @@ tc_score_kernel(const __grid_constant__ CUtensorMap tm_users, const __grid_const
       mbar_wait(bar_tfull + acc, (t >> 1) & 1);
       fence_after_sync();
       const int n0 = t * TC_TN;
-      const uint32_t tbase = tmem + ((uint32_t)(quarter * 32) << 16) + acc * 256 + half * 128;
-      // two register buffers: the load of group g+1 is in flight while group g is processed
+      const uint32_t tbase = tmem + ((uint32_t)(quarter * 32) << 16) + acc * 256 + half * 128 + chalf * 64;
+      const int c0 = n0 + chalf * 64;
+      // two register buffers: the load of the second group is in flight while the first is processed
       uint32_t r0[32], r1[32];
       tmem_ld_32x32(tbase, r0);
       tmem_ld_wait();
       tmem_ld_32x32(tbase + 32, r1);
-      process_group(r0, n0);
+      process_group(r0, c0);
       tmem_ld_wait();
-      tmem_ld_32x32(tbase + 64, r0);
-      process_group(r1, n0 + 32);
-      tmem_ld_wait();
-      tmem_ld_32x32(tbase + 96, r1);
-      process_group(r0, n0 + 64);
-      tmem_ld_wait();
-      process_group(r1, n0 + 96);
-      fence_before_sync();
+      fence_before_sync();  // my share of the accumulator is in registers: hand the stage back before selecting
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + acc);
+      process_group(r1, c0 + 32);
     }
     if (active) {
-      for (int p = 0; p < TC_CAND; ++p) {
-        a.cand_s[(size_t)q * TC_CAND + p] = (p < cnt) ? cs[p * 256 + tix] : -INFINITY;
-        a.cand_i[(size_t)q * TC_CAND + p] = (p < cnt) ? ci[p * 256 + tix] : -1;
+      const size_t o = ((size_t)q * 2 + chalf) * TC_LIST;
+      for (int p = 0; p < TC_LIST; ++p) {
+        a.cand_s[o + p] = (p < cnt) ? cs[p * 512 + tix] : -INFINITY;
+        a.cand_i[o + p] = (p < cnt) ? ci[p * 512 + tix] : -1;
       }
-      a.cand_n[q] = cnt;
-      a.cand_thr[q] = (cnt == TC_CAND) ? thr : -INFINITY;
+      a.cand_n[(size_t)q * 2 + chalf] = cnt;
+      a.cand_thr[(size_t)q * 2 + chalf] = (cnt == TC_LIST) ? thr : -INFINITY;
     }
   }
   fence_before_sync();
@@ -331,41 +328,56 @@ __global__ void __launch_bounds__(256) tc_rescore_kernel(const RescoreArgs a) {
   const int lane = threadIdx.x & 31;
   const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (q >= a.n_q) return;
-  const int cnt = a.cand_n[q];
-  const int id = (lane < cnt) ? a.cand_i[(size_t)q * TC_CAND + lane] : 0x7fffffff;
-  // exact score: the same fp32 fma chain over k = 0..63 as impl 1 and the oracle
-  float s = -INFINITY;
-  if (lane < cnt) {
-    const float* u = a.ug + (size_t)q * TC_D;
-    const float* it = a.item_emb + (size_t)id * TC_D;
-    float acc = 0.f;
-#pragma unroll 4
-    for (int k4 = 0; k4 < TC_D / 4; ++k4) {
-      const float4 uv = *reinterpret_cast<const float4*>(u + k4 * 4);
-      const float4 iv = ldg4(it + k4 * 4);
-      acc = fmaf(uv.x, iv.x, acc);
-      acc = fmaf(uv.y, iv.y, acc);
-      acc = fmaf(uv.z, iv.z, acc);
-      acc = fmaf(uv.w, iv.w, acc);
-    }
-    s = acc;
-  }
-  // rank of my candidate by item id (ids are distinct)
-  int rank = 0;
+  const int cnt_a = a.cand_n[(size_t)q * 2], cnt_b = a.cand_n[(size_t)q * 2 + 1];
+  const int cnt = cnt_a + cnt_b;
+  // 48 candidate slots (24 per column half) on 32 lanes: lane l owns slots l and l + 32
+  int id[2];
+  float s[2];
+  bool mine[2];
 #pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int c = lane + 32 * h;
+    mine[h] = c < TC_CAND && (c % TC_LIST) < ((c < TC_LIST) ? cnt_a : cnt_b);
+    id[h] = mine[h] ? a.cand_i[(size_t)q * TC_CAND + c] : 0x7fffffff;
+    // exact score: the same fp32 fma chain over k = 0..63 as impl 1 and the oracle
+    s[h] = -INFINITY;
+    if (mine[h]) {
+      const float* u = a.ug + (size_t)q * TC_D;
+      const float* it = a.item_emb + (size_t)id[h] * TC_D;
+      float acc = 0.f;
+#pragma unroll 4
+      for (int k4 = 0; k4 < TC_D / 4; ++k4) {
+        const float4 uv = *reinterpret_cast<const float4*>(u + k4 * 4);
+        const float4 iv = ldg4(it + k4 * 4);
+        acc = fmaf(uv.x, iv.x, acc);
+        acc = fmaf(uv.y, iv.y, acc);
+        acc = fmaf(uv.z, iv.z, acc);
+        acc = fmaf(uv.w, iv.w, acc);
+      }
+      s[h] = acc;
+    }
+  }
+  // rank of my candidates by item id (ids are distinct; empty slots carry INT_MAX and never count)
+  int rank[2] = {0, 0};
+#pragma unroll 8
   for (int l = 0; l < 32; ++l) {
-    const int oid = __shfl_sync(SRB_FULL_MASK, id, l);
-    rank += (oid < id) ? 1 : 0;
+    const int o0 = __shfl_sync(SRB_FULL_MASK, id[0], l);
+    const int o1 = __shfl_sync(SRB_FULL_MASK, id[1], l);
+    rank[0] += (o0 < id[0]) + (o1 < id[0]);
+    rank[1] += (o0 < id[1]) + (o1 < id[1]);
   }
   // find_k_largest's sequential process over the candidates in id order (see score_topk.cu)
   const int K = a.k;
   float ls = -INFINITY;
   int li = -1;
   for (int t = 0; t < cnt; ++t) {
-    const unsigned who = __ballot_sync(SRB_FULL_MASK, lane < cnt && rank == t);
-    const int src = __ffs(who) - 1;
-    const float cs = __shfl_sync(SRB_FULL_MASK, s, src);
-    const int cid = __shfl_sync(SRB_FULL_MASK, id, src);
+    const unsigned w0 = __ballot_sync(SRB_FULL_MASK, mine[0] && rank[0] == t);
+    const unsigned w1 = __ballot_sync(SRB_FULL_MASK, mine[1] && rank[1] == t);
+    const int src = __ffs(w0 ? w0 : w1) - 1;
+    const float c0 = __shfl_sync(SRB_FULL_MASK, s[0], src), c1 = __shfl_sync(SRB_FULL_MASK, s[1], src);
+    const int d0 = __shfl_sync(SRB_FULL_MASK, id[0], src), d1 = __shfl_sync(SRB_FULL_MASK, id[1], src);
+    const float cs = w0 ? c0 : c1;
+    const int cid = w0 ? d0 : d1;
     const float thr = __shfl_sync(SRB_FULL_MASK, ls, K - 1);
     if (cs > thr) {
       const int pos = __popc(__ballot_sync(SRB_FULL_MASK, lane < K && ls > cs));
@@ -379,7 +391,7 @@ __global__ void __launch_bounds__(256) tc_rescore_kernel(const RescoreArgs a) {
   const float kth = __shfl_sync(SRB_FULL_MASK, ls, K - 1);
   const float bmax = __uint_as_float(*a.bmax_bits);
   const float E = (1.0f / 512.0f + 1.0f / 65536.0f + 1.0f / 262144.0f) * a.unorm[q] * bmax;  // TF32 truncation + slot tags
-  const float thr32 = a.cand_thr[q];
+  const float thr32 = fmaxf(a.cand_thr[(size_t)q * 2], a.cand_thr[(size_t)q * 2 + 1]);
   int deg = 0;
   if (a.rated_ptr) {
     const int u = a.users[q];
@@ -439,8 +451,8 @@ static TcWorkspace tc_carve(char* base, int n_q, int n_items) {
   w.bmax = (unsigned int*)take(16);
   w.cand_s = (float*)take((int64_t)n_q * TC_CAND * 4);
   w.cand_i = (int32_t*)take((int64_t)n_q * TC_CAND * 4);
-  w.cand_n = (int32_t*)take((int64_t)n_q * 4);
-  w.cand_thr = (float*)take((int64_t)n_q * 4);
+  w.cand_n = (int32_t*)take((int64_t)n_q * 2 * 4);
+  w.cand_thr = (float*)take((int64_t)n_q * 2 * 4);
   w.fb_count = (int32_t*)take(16);
   w.fb_rows = (int32_t*)take((int64_t)n_q * 4);
   w.fb_users = (int32_t*)take((int64_t)n_q * 4);

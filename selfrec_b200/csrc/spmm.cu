@@ -156,48 +156,82 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmArgs& a, int row, int gl
 // Each lane loads one (col, val) pair per iteration (coalesced, prefetched one iteration ahead) and
 // the pairs are walked with group-wide shuffles; every X-row gather is two 128-bit ld.global.nc per
 // lane (LPR lanes x 16 B = one contiguous half row), issued 2*SB at a time before the FMAs.
-template <int D>
+template <int D, bool MASKED>
 __device__ __forceinline__ void spmm_gather(const SpmmArgs& a, int p, int end, int stride, int gl, float4& acc0, float4& acc1) {
   constexpr int LPR = D / 8;
   constexpr int HALF = D / 2;
   constexpr int SB = LPR < 4 ? LPR : 4;  // sub-batch: 2*SB independent 128-bit gathers per lane in flight
+  constexpr bool masked = MASKED;  // compile-time: the plain product must not pay for the mask logic
+  const int lane = threadIdx.x & 31;
+  const int gbase = lane - gl;  // first lane of my group
   // (col, val) of the current iteration; padding slots gather row 0 with weight 0 (an L1 hit)
   int c = 0;
   float v = 0.f;
+  bool hit = false;
   if (p + gl < end) {
     c = __ldg(a.colidx + p + gl);
     v = __ldg(a.vals + p + gl);
-    if (a.col_mask && !((__ldg(a.col_mask + (c >> 5)) >> (c & 31)) & 1u)) c = 0, v = 0.f;
+    if (masked) hit = (__ldg(a.col_mask + (c >> 5)) >> (c & 31)) & 1u;
   }
   while (__any_sync(SRB_FULL_MASK, p < end)) {
     int cn = 0;
     float vn = 0.f;
+    bool hitn = false;
     if (p + stride + gl < end) {  // prefetch the next iteration's pair
       cn = __ldg(a.colidx + p + stride + gl);
       vn = __ldg(a.vals + p + stride + gl);
-      if (a.col_mask && !((__ldg(a.col_mask + (cn >> 5)) >> (cn & 31)) & 1u)) cn = 0, vn = 0.f;
+      if (masked) hitn = (__ldg(a.col_mask + (cn >> 5)) >> (cn & 31)) & 1u;
     }
+    if (!masked) {
 #pragma unroll
-    for (int j0 = 0; j0 < LPR; j0 += SB) {
-      if (j0 > 0 && !__any_sync(SRB_FULL_MASK, p + j0 < end)) break;
-      float vv[SB];
-      float4 x0[SB], x1[SB];
+      for (int j0 = 0; j0 < LPR; j0 += SB) {
+        if (j0 > 0 && !__any_sync(SRB_FULL_MASK, p + j0 < end)) break;
+        float vv[SB];
+        float4 x0[SB], x1[SB];
 #pragma unroll
-      for (int j = 0; j < SB; ++j) {
-        const int cc = __shfl_sync(SRB_FULL_MASK, c, j0 + j, LPR);
-        vv[j] = __shfl_sync(SRB_FULL_MASK, v, j0 + j, LPR);
-        const float* xr = a.X + (size_t)cc * D + gl * 4;
-        x0[j] = ldg4(xr);
-        x1[j] = ldg4(xr + HALF);
+        for (int j = 0; j < SB; ++j) {
+          const int cc = __shfl_sync(SRB_FULL_MASK, c, j0 + j, LPR);
+          vv[j] = __shfl_sync(SRB_FULL_MASK, v, j0 + j, LPR);
+          const float* xr = a.X + (size_t)cc * D + gl * 4;
+          x0[j] = ldg4(xr);
+          x1[j] = ldg4(xr + HALF);
+        }
+#pragma unroll
+        for (int j = 0; j < SB; ++j) {
+          acc0 = f4_fma(vv[j], x0[j], acc0);
+          acc1 = f4_fma(vv[j], x1[j], acc1);
+        }
       }
+    } else {
+      // row-sparse X: only the non-zeros whose column bit is set are gathered.  Each lane group compacts its
+      // hits (ballot + find-first-set) so a sub-batch holds SB real gathers; the warp stops when every
+      // group has run out -- fewer dependent L2 round trips, which is what bounds this product
+      uint32_t gm = (__ballot_sync(SRB_FULL_MASK, hit) >> gbase) & ((1u << LPR) - 1u);
+      while (__any_sync(SRB_FULL_MASK, gm != 0)) {
+        float vv[SB];
+        float4 x0[SB], x1[SB];
 #pragma unroll
-      for (int j = 0; j < SB; ++j) {
-        acc0 = f4_fma(vv[j], x0[j], acc0);
-        acc1 = f4_fma(vv[j], x1[j], acc1);
+        for (int j = 0; j < SB; ++j) {
+          const int src = gm ? (__ffs(gm) - 1) : 0;
+          const bool live = gm != 0;
+          gm &= gm - 1;
+          const int cc = __shfl_sync(SRB_FULL_MASK, c, gbase + src);
+          const float vs = __shfl_sync(SRB_FULL_MASK, v, gbase + src);
+          vv[j] = live ? vs : 0.f;
+          const float* xr = a.X + (size_t)(live ? cc : 0) * D + gl * 4;
+          x0[j] = ldg4(xr);
+          x1[j] = ldg4(xr + HALF);
+        }
+#pragma unroll
+        for (int j = 0; j < SB; ++j) {
+          acc0 = f4_fma(vv[j], x0[j], acc0);
+          acc1 = f4_fma(vv[j], x1[j], acc1);
+        }
       }
     }
     c = cn;
     v = vn;
+    hit = hitn;
     p += stride;
   }
 }
@@ -215,7 +249,7 @@ __device__ __forceinline__ void xor_reduce_groups(float4& acc0, float4& acc1, in
   }
 }
 
-template <int D>
+template <int D, bool MASKED>
 __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmArgs a) {
   constexpr int LPR = D / 8;     // lanes per row
   constexpr int RPW = 32 / LPR;  // rows per warp (short rows)
@@ -248,7 +282,7 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmArgs a) {
     const int wbeg = beg + wib * per;
     const int wend = min(end, wbeg + per);
     float4 acc0 = f4_zero(), acc1 = f4_zero();
-    spmm_gather<D>(a, wbeg + grp * LPR, wend, 32, gl, acc0, acc1);
+    spmm_gather<D, MASKED>(a, wbeg + grp * LPR, wend, 32, gl, acc0, acc1);
     xor_reduce_groups(acc0, acc1, LPR);
     if (grp == 0) {
       part[wib][0][gl] = acc0;
@@ -283,7 +317,7 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmArgs a) {
     }
     if (is_long) p += grp * LPR;
     float4 acc0 = f4_zero(), acc1 = f4_zero();
-    spmm_gather<D>(a, p, end, is_long ? 32 : LPR, gl, acc0, acc1);
+    spmm_gather<D, MASKED>(a, p, end, is_long ? 32 : LPR, gl, acc0, acc1);
     if (is_long) {  // combine the lane groups; group 0 owns the row
       xor_reduce_groups(acc0, acc1, LPR);
       valid = valid && grp == 0;
@@ -302,10 +336,11 @@ static int launch_spmm(const SpmmArgs& a, int d, cudaStream_t st) {
   if (blocks < a.n_vlong) blocks = a.n_vlong;
   const long long cap = (long long)sm_count() * 8;  // 8 x 256 threads = full residency
   if (blocks > cap) blocks = cap;
+  const bool m = a.col_mask != nullptr;
   switch (d) {
-    case 32: spmm_csr_kernel<32><<<(int)blocks, threads, 0, st>>>(a); break;
-    case 64: spmm_csr_kernel<64><<<(int)blocks, threads, 0, st>>>(a); break;
-    case 128: spmm_csr_kernel<128><<<(int)blocks, threads, 0, st>>>(a); break;
+    case 32: m ? spmm_csr_kernel<32, true><<<(int)blocks, threads, 0, st>>>(a) : spmm_csr_kernel<32, false><<<(int)blocks, threads, 0, st>>>(a); break;
+    case 64: m ? spmm_csr_kernel<64, true><<<(int)blocks, threads, 0, st>>>(a) : spmm_csr_kernel<64, false><<<(int)blocks, threads, 0, st>>>(a); break;
+    case 128: m ? spmm_csr_kernel<128, true><<<(int)blocks, threads, 0, st>>>(a) : spmm_csr_kernel<128, false><<<(int)blocks, threads, 0, st>>>(a); break;
     default: set_error("spmm: unsupported d=%d (32, 64, 128)", d); return SRB_ERR_ARG;
   }
   return post_launch("spmm_csr_kernel");

@@ -37,6 +37,65 @@ __global__ void gather_rows(const float* __restrict__ tab, const int* __restrict
   if (acc == 123.456f) *sink = acc;
 }
 
+
+// the same gather through the TMA unit: every lane issues one cp.async.bulk of a whole row into the warp's
+// shared-memory ring (ST stages of 32 rows); completion by mbarrier transaction count; the rows are then read
+// back from shared memory (ld.shared.v4) like an SpMM would.
+template <int ROWB, int ST>
+__global__ void __launch_bounds__(256) gather_rows_bulk(const float* __restrict__ tab, const int* __restrict__ idx, size_t n_idx, float* sink) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int WARPS = 8;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  unsigned char* ring = smem_raw + (size_t)w * ST * 32 * ROWB;
+  __shared__ unsigned long long bars[WARPS][ST];
+  if (lane == 0)
+    for (int s = 0; s < ST; ++s) {
+      unsigned a = (unsigned)__cvta_generic_to_shared(&bars[w][s]);
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(a));
+    }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncwarp();
+  const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  float acc = 0.f;
+  size_t n_it = 0;
+  for (size_t base = warp * 32; base + 32 <= n_idx; base += nwarps * 32) ++n_it;
+  auto issue = [&](size_t it) {
+    const int s = (int)(it % ST);
+    const size_t base = (warp + it * nwarps) * 32;
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&bars[w][s]);
+    if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(32 * ROWB) : "memory");
+    __syncwarp();
+    const int r = __ldg(idx + base + lane);
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(ring + ((size_t)s * 32 + lane) * ROWB);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(tab + (size_t)r * (ROWB / 4)), "r"(ROWB), "r"(bar)
+                 : "memory");
+  };
+  for (size_t it = 0; it < (size_t)(ST - 1) && it < n_it; ++it) issue(it);
+  for (size_t it = 0; it < n_it; ++it) {
+    if (it + ST - 1 < n_it) issue(it + ST - 1);
+    const int s = (int)(it % ST);
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&bars[w][s]);
+    const unsigned parity = (unsigned)((it / ST) & 1);
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\tWAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+    // read the stage back: lane l reads 16 bytes of every row (the SpMM's lane-group mapping reads as much)
+    const float4* st = reinterpret_cast<const float4*>(ring + (size_t)s * 32 * ROWB);
+#pragma unroll 8
+    for (int k = lane; k < 32 * ROWB / 16; k += 32) {
+      const float4 v = st[k];
+      acc += v.x + v.y + v.z + v.w;
+    }
+    __syncwarp();
+  }
+  if (acc == 123.456f) *sink = acc;
+}
+
 template <typename F>
 float time_ms(F f, int iters) {
   cudaEvent_t a, b;
@@ -95,6 +154,20 @@ int main() {
     RUN(128, 8, 8)
     RUN(512, 4, 8)
     RUN(512, 8, 8)
+#define RUNB(ROWB, ST, BLK)                                                                                         \
+  {                                                                                                                 \
+    const size_t smem = (size_t)8 * ST * 32 * ROWB;                                                                 \
+    cudaFuncSetAttribute(gather_rows_bulk<ROWB, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
+    float ms = time_ms([&] { gather_rows_bulk<ROWB, ST><<<sms * BLK, 256, smem>>>(tab, idx, n_idx, sink); }, 10);   \
+    printf("bulk   rows=%8zu rowB=%3d stages=%d blk/SM=%d smem/blk=%3zu KB: %8.1f GB/s  (%s)\n", rows, ROWB, ST, BLK, smem >> 10, \
+           n_idx * (double)ROWB / ms / 1e6, cudaGetErrorString(cudaGetLastError()));                                \
+  }
+    if (rows <= 262144) {
+      RUNB(256, 2, 3)
+      RUNB(256, 3, 2)
+      RUNB(256, 2, 1)
+      RUNB(256, 3, 1)
+    }
     cudaFree(idx);
     cudaFree(tab);
   }
