@@ -343,16 +343,18 @@ __global__ void __launch_bounds__(256) tc_rescore_kernel(const RescoreArgs a) {
     s[h] = -INFINITY;
     if (mine[h]) {
       const float* u = a.ug + (size_t)q * TC_D;
-      const float* it = a.item_emb + (size_t)id[h] * TC_D;
+      const float4* it = reinterpret_cast<const float4*>(a.item_emb + (size_t)id[h] * TC_D);
+      float4 iv[TC_D / 4];  // the whole row in flight at once: this kernel is bound by the latency of these gathers
+#pragma unroll
+      for (int k4 = 0; k4 < TC_D / 4; ++k4) iv[k4] = __ldg(it + k4);
       float acc = 0.f;
-#pragma unroll 4
+#pragma unroll
       for (int k4 = 0; k4 < TC_D / 4; ++k4) {
         const float4 uv = *reinterpret_cast<const float4*>(u + k4 * 4);
-        const float4 iv = ldg4(it + k4 * 4);
-        acc = fmaf(uv.x, iv.x, acc);
-        acc = fmaf(uv.y, iv.y, acc);
-        acc = fmaf(uv.z, iv.z, acc);
-        acc = fmaf(uv.w, iv.w, acc);
+        acc = fmaf(uv.x, iv[k4].x, acc);
+        acc = fmaf(uv.y, iv[k4].y, acc);
+        acc = fmaf(uv.z, iv[k4].z, acc);
+        acc = fmaf(uv.w, iv[k4].w, acc);
       }
       s[h] = acc;
     }
