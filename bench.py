@@ -485,7 +485,8 @@ def run_sharded(args, rank, world, local_rank, data):
         "data": "synthetic",
         "config": {"workload": "XSimGCL yelp2018-shape 31668x38048x1237259, L=3 d=64 B=2048 tau=0.2 lambda=0.2 eps=0.2 l*=1",
                    "parallelism": f"row-sharded x{world}: nnz-balanced row blocks, SpMM epilogue pushes each layer to all ranks over "
-                                  "NVLink (fused all-gather), 2L+1 device-side barriers per step, batch losses replicated",
+                                  f"NVLink ({'one NVSwitch-multicast store per row' if sh.prop.use_mc else 'one P2P store per row and rank'}, "
+                                  "fused all-gather), 2L+1 device-side barriers per step, batch losses replicated",
                    "l2": "no flush: per-step working set > 126 MB L2",
                    "inputs": f"{P} pre-sampled batches resident in HBM on every rank; {mode}"},
         "clocks": clk,

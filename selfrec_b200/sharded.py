@@ -82,6 +82,12 @@ class ShardedPropagator:
             t.zero_()
             self.bufs.append(t)
             self.handles.append(h)
+        # NVSwitch multicast (NVLS): one store to the multicast mapping of a symmetric buffer lands in every
+        # rank's copy, so the SpMM epilogue issues 1 store per row instead of `world` and each GPU's NVLink
+        # egress drops from (world-1)/world of a layer to 1/world of it.  SRB_MULTICAST=0 forces unicast.
+        import os
+        self.mc = [int(getattr(h, "multicast_ptr", 0) or 0) for h in self.handles]
+        self.use_mc = self.world > 1 and all(m != 0 for m in self.mc) and os.environ.get("SRB_MULTICAST", "1") != "0"
         torch.cuda.synchronize()
         dist.barrier(self.group)
 
@@ -115,9 +121,12 @@ class ShardedPropagator:
                 setattr(loc, k, ops._p(v))
             else:
                 setattr(loc, k, v)
-        sd.row_begin, sd.world = self.shard.row_begin, self.world
+        sd.row_begin, sd.world = self.shard.row_begin, (1 if self.use_mc else self.world)
         for idx, field in ((push_y, "peer_Y"), (push_sum, "peer_sum"), (push_p, "peer_p")):
             if idx is not None:
+                if self.use_mc:
+                    getattr(sd, field)[0] = self.mc[idx]  # the one "peer" is the multicast address
+                    continue
                 arr = self.peer_ptrs(idx)
                 for g in range(self.world):
                     getattr(sd, field)[g] = arr[g]
