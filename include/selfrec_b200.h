@@ -302,6 +302,12 @@ int srb_score_rows(const float* user_emb, const float* item_emb, int32_t d, cons
 int srb_topk_rows(const float* scores, int32_t n_q, int32_t n_items, int32_t k, int32_t* out_ids,
                   float* out_scores, void* stream);
 
+/* random.sample(range(n), k) on a CPython MT19937 state (624 words + index, as random.getstate()[1]):
+ * the draw behind GraphAugmentor.node_dropout / edge_dropout (data/augmentor.py:16-17, 28).  use_pool
+ * selects CPython's pool-list variant (n <= setsize) or its selected-set variant; the state is advanced
+ * exactly as CPython would. */
+int srb_random_sample_range(uint32_t* mt625, int64_t n, int64_t k, int32_t use_pool, int64_t* out);
+
 /* ---------------------------------------------------------------------------------------
  * Native dataset -> CSR builder (host C++).  Replaces the Python loops of
  *   FileIO.load_data_set (data/loader.py:23-33), Interaction.__generate_set (data/ui_graph.py:29-45),

@@ -285,3 +285,51 @@ extern "C" int64_t srb_sampler_epoch(srb_sampler* s, int32_t batch_size, int32_t
   s->epoch_open = false;
   return nb;
 }
+
+
+// random.sample(range(n), k) on an MT19937 state (data/augmentor.py:16-17,28: SGL's node / edge dropout draws
+// its survivors this way every epoch; 1.1 M draws at yelp2018).  Both CPython strategies (Lib/random.py
+// sample()): `use_pool` != 0 -> the pool-list variant (n <= setsize), else the selected-set variant with
+// re-draws.  The caller decides which, with CPython's own float expression for setsize.  mt625 is updated.
+extern "C" int srb_random_sample_range(uint32_t* mt625, int64_t n, int64_t k, int32_t use_pool, int64_t* out) {
+  if (!mt625 || (k > 0 && !out)) {
+    srb::set_error("random_sample_range: null pointer");
+    return SRB_ERR_ARG;
+  }
+  if (k < 0 || k > n || n >= (int64_t)1 << 32) {
+    srb::set_error("random_sample_range: need 0 <= k <= n < 2^32 (k=%lld n=%lld)", (long long)k, (long long)n);
+    return SRB_ERR_ARG;
+  }
+  if (mt625[624] > 624) {
+    srb::set_error("random_sample_range: bad MT index %u", mt625[624]);
+    return SRB_ERR_ARG;
+  }
+  srb_sampler* g = new (std::nothrow) srb_sampler();
+  if (!g) {
+    srb::set_error("random_sample_range: out of memory");
+    return SRB_ERR_ARG;
+  }
+  memcpy(g->mt, mt625, 624 * 4);
+  g->mti = (int)mt625[624];
+  if (use_pool) {
+    std::vector<int64_t> pool((size_t)n);
+    for (int64_t i = 0; i < n; ++i) pool[(size_t)i] = i;
+    for (int64_t i = 0; i < k; ++i) {
+      const int64_t j = (int64_t)g->randbelow((uint32_t)(n - i));
+      out[i] = pool[(size_t)j];
+      pool[(size_t)j] = pool[(size_t)(n - i - 1)];  // move a non-selected item into the vacancy
+    }
+  } else {
+    std::vector<uint64_t> seen((size_t)((n + 63) / 64), 0);
+    for (int64_t i = 0; i < k; ++i) {
+      uint32_t j = g->randbelow((uint32_t)n);
+      while (seen[j >> 6] >> (j & 63) & 1) j = g->randbelow((uint32_t)n);
+      seen[j >> 6] |= (uint64_t)1 << (j & 63);
+      out[i] = (int64_t)j;
+    }
+  }
+  memcpy(mt625, g->mt, 624 * 4);
+  mt625[624] = (uint32_t)g->mti;
+  delete g;
+  return SRB_OK;
+}

@@ -368,25 +368,30 @@ __global__ void __launch_bounds__(256) tc_rescore_kernel(const RescoreArgs a) {
     rank[0] += (o0 < id[0]) + (o1 < id[0]);
     rank[1] += (o0 < id[1]) + (o1 < id[1]);
   }
-  // find_k_largest's sequential process over the candidates in id order (see score_topk.cu)
+  // find_k_largest's sequential process over the candidates in id order (see score_topk.cu).  The candidates
+  // are first laid out in id order in shared memory, so that each step is one broadcast load and a
+  // warp-uniform compare instead of a ballot / find-first-set / shuffle chain
+  __shared__ float2 ord[8][TC_CAND];
+  float2* mo = ord[threadIdx.x >> 5];
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+    if (mine[h]) mo[rank[h]] = make_float2(s[h], __int_as_float(id[h]));
+  __syncwarp();
   const int K = a.k;
   float ls = -INFINITY;
   int li = -1;
+  float thr = -INFINITY;  // score of list slot K-1 (warp-uniform)
   for (int t = 0; t < cnt; ++t) {
-    const unsigned w0 = __ballot_sync(SRB_FULL_MASK, mine[0] && rank[0] == t);
-    const unsigned w1 = __ballot_sync(SRB_FULL_MASK, mine[1] && rank[1] == t);
-    const int src = __ffs(w0 ? w0 : w1) - 1;
-    const float c0 = __shfl_sync(SRB_FULL_MASK, s[0], src), c1 = __shfl_sync(SRB_FULL_MASK, s[1], src);
-    const int d0 = __shfl_sync(SRB_FULL_MASK, id[0], src), d1 = __shfl_sync(SRB_FULL_MASK, id[1], src);
-    const float cs = w0 ? c0 : c1;
-    const int cid = w0 ? d0 : d1;
-    const float thr = __shfl_sync(SRB_FULL_MASK, ls, K - 1);
+    const float2 e = mo[t];
+    const float cs = e.x;
     if (cs > thr) {
+      const int cid = __float_as_int(e.y);
       const int pos = __popc(__ballot_sync(SRB_FULL_MASK, lane < K && ls > cs));
       const float ps = __shfl_up_sync(SRB_FULL_MASK, ls, 1);
       const int pi = __shfl_up_sync(SRB_FULL_MASK, li, 1);
       if (lane > pos && lane < K) ls = ps, li = pi;
       if (lane == pos) ls = cs, li = cid;
+      thr = __shfl_sync(SRB_FULL_MASK, ls, K - 1);
     }
   }
   // exactness test

@@ -285,6 +285,40 @@ def test_native_dataset_builder_errors(built_lib, tmp_path):
         load_interaction(None, bad)
 
 
+@pytest.mark.parametrize("n,k", [(10, 0), (10, 10), (10, 3), (100, 6), (100, 90), (5000, 4500), (5000, 7), (22, 21), (21, 5), (87, 6),
+                                 (300000, 270000), (300000, 50)])
+def test_native_random_sample_is_cpython_exact(built_lib, n, k):
+    """srb_random_sample_range == random.sample(range(n), k): same draws in the same order (both CPython
+    strategies: pool list and selected set) and the same generator state afterwards."""
+    from selfrec_b200.data.augmentor import sample_range
+    random.seed(n * 7 + k)
+    want = random.sample(range(n), k)
+    st_want = random.getstate()
+    random.seed(n * 7 + k)
+    got = sample_range(n, k)
+    assert got.tolist() == want and random.getstate() == st_want
+    with pytest.raises(ValueError):
+        sample_range(5, 6)
+
+
+def test_sgl_views_match_reference_graphs(built_lib, golden, tiny_triples, tiny_conf, in_tmp_cwd):
+    """R11: the two edge-dropped, re-normalised graphs SGL builds for an epoch (SGL.py:80-96,
+    data/augmentor.py:23-32, ui_graph.py:58-65) equal the reference's own, bit for bit, when Python's
+    `random` starts from the same seed -- through the native sampler of random.sample."""
+    from selfrec_b200.data.augmentor import GraphAugmentor
+    from selfrec_b200.data.ui_graph import Interaction
+    train, test = tiny_triples
+    fx = golden("train_SGL.npz")
+    d = Interaction(tiny_conf("SGL"), [list(t) for t in train], [list(t) for t in test])
+    random.seed(1000 + len("SGL"))  # oracle/gen_golden.py seeds the reference run this way
+    n = d.user_num + d.item_num
+    for k in range(2):
+        dropped = GraphAugmentor.edge_dropout(d.interaction_mat, 0.1)
+        lap = d.convert_to_laplacian_mat(dropped)
+        ref = sp.csr_matrix((fx[f"view{k}_data"], fx[f"view{k}_indices"], fx[f"view{k}_indptr"]), shape=(n, n))
+        assert _same_csr(lap, ref), k
+
+
 def test_install_aliases_boundary_modules(built_lib):
     import sys
     import selfrec_b200
