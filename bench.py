@@ -547,9 +547,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        if args.steps > 20:
-            args.steps = 20  # bounded sample: ~1 s per CPU step
-        args.warmup = min(args.warmup, 2)
+        if args.steps > 8:
+            args.steps = 8  # bounded sample: 2.5-13 s per CPU step depending on the host
+        args.warmup = min(args.warmup, 1)
         run_reference(args, rank, world)
         return
     if world > 1:
