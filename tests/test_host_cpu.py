@@ -319,6 +319,37 @@ def test_sgl_views_match_reference_graphs(built_lib, golden, tiny_triples, tiny_
         assert _same_csr(lap, ref), k
 
 
+def test_ctypes_structs_match_the_header_layout(tmp_path):
+    """Every ctypes.Structure in _lib.py must have the size and field offsets of the C struct it mirrors in
+    include/selfrec_b200.h (a drifted field would silently shift every pointer after it): gcc prints
+    sizeof / offsetof for each field, ctypes must agree."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    from selfrec_b200 import _lib
+    pairs = {"srb_spmm_desc": _lib.SpmmDesc, "srb_encoder_desc": _lib.EncoderDesc, "srb_scatter_seg": _lib.ScatterSeg,
+             "srb_bpr_desc": _lib.BprDesc, "srb_infonce_problem": _lib.InfoNceProblem, "srb_infonce_desc": _lib.InfoNceDesc,
+             "srb_topk_desc": _lib.TopkDesc, "srb_graph_csr": _lib.GraphCsr, "srb_step_desc": _lib.StepDesc,
+             "srb_spmm_sharded_desc": _lib.SpmmShardedDesc}
+    cc = shutil.which("gcc") or shutil.which("cc")
+    assert cc, "a C compiler is part of the toolchain"
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "selfrec_b200.h"', 'int main(void) {']
+    for cname, st in pairs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _t in st._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run([cc, "-I", os.path.join(os.path.dirname(GOLDEN), "..", "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, st in pairs.items():
+        assert int(out[cname]) == C.sizeof(st), cname
+        for fname, _t in st._fields_:
+            assert int(out[f"{cname}.{fname}"]) == getattr(st, fname).offset, f"{cname}.{fname}"
+
+
 def test_install_aliases_boundary_modules(built_lib):
     import sys
     import selfrec_b200
