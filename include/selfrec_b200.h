@@ -308,6 +308,16 @@ int srb_topk_rows(const float* scores, int32_t n_q, int32_t n_items, int32_t k, 
  * exactly as CPython would. */
 int srb_random_sample_range(uint32_t* mt625, int64_t n, int64_t k, int32_t use_pool, int64_t* out);
 
+/* Rows of the [N, d] tables a batch touches (u, U + i, U + j; batch = srb_sampler_next_batch layout), listed for
+ * srb_spmm_desc.n_vlong_dev: rows[3][3*batch_cap] by degree class (a CTA per long row, a warp per other row),
+ * counters[4] = class sizes, row_mask (optional, (n_total_rows+31)/32 words) = bitmap of all batch rows for
+ * srb_spmm_desc.col_mask.  Row-sharded tables: only rows in [row_begin, row_begin + n_local_rows) are listed, as
+ * local ids of the rank's CSR slice (rowptr).  This is what lets the last forward layer of a training step
+ * (nothing but the batch rows of the final mean is read, XSimGCL.py:30,45-50) skip every other row. */
+int srb_build_batch_rows(const int32_t* batch, int32_t batch_cap, int32_t n_users, const int32_t* rowptr,
+                         int32_t row_begin, int32_t n_local_rows, int32_t n_total_rows, int32_t* rows,
+                         int32_t* counters, uint32_t* row_mask, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Native dataset -> CSR builder (host C++).  Replaces the Python loops of
  *   FileIO.load_data_set (data/loader.py:23-33), Interaction.__generate_set (data/ui_graph.py:29-45),

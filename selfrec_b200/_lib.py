@@ -124,6 +124,7 @@ SYMBOLS = {
     "srb_scatter_add_segments": (C.c_int, [VP, C.c_int32, C.c_int32, VP, VP]),
     "srb_rank_hit_masks": (C.c_int, [VP, C.c_int32, C.c_int32, VP, VP, VP, VP, VP]),
     "srb_random_sample_range": (C.c_int, [VP, C.c_int64, C.c_int64, C.c_int32, VP]),
+    "srb_build_batch_rows": (C.c_int, [VP, C.c_int32, C.c_int32, VP, C.c_int32, C.c_int32, C.c_int32, VP, VP, VP, VP]),
     "srb_dataset_load": (VP, [C.c_char_p, C.c_char_p]),
     "srb_dataset_free": (None, [VP]),
     "srb_dataset_counts": (C.c_int, [VP, VP]),

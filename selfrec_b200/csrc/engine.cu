@@ -119,14 +119,20 @@ __global__ void build_cat_idx_kernel(const int32_t* batch, int cap, int n_users,
 // last-layer SpMM (a CTA per long row, a warp per other row; the lane-group class stays empty) into
 // three segments of capacity 3*cap; counters[c] ends up as the size of class c.  Also sets the rows'
 // bits in row_mask.  counters[0..3] and row_mask are zeroed by the caller.
+// With a row range [row_begin, row_begin + n_local) (row-sharded tables) only the rows of that range are listed,
+// as LOCAL row ids of the rank's CSR slice; the bitmap always covers all batch rows (global ids).
 __global__ void __launch_bounds__(256) build_batch_rows_kernel(const int32_t* batch, int cap, int n_users, const int32_t* rowptr,
-                                                               int32_t* rows, int32_t* counters, uint32_t* row_mask) {
+                                                               int row_begin, int n_local, int32_t* rows, int32_t* counters,
+                                                               uint32_t* row_mask) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = min(batch[0], cap);
   const int sec = t / cap, k = t % cap;
   if (sec >= 3 || k >= b) return;
   const int32_t* u = batch + SRB_BATCH_HEADER;
-  const int row = (sec == 0) ? u[k] : n_users + u[sec * cap + k];
+  const int grow = (sec == 0) ? u[k] : n_users + u[sec * cap + k];
+  if (row_mask) atomicOr(row_mask + (grow >> 5), 1u << (grow & 31));
+  const int row = grow - row_begin;
+  if (row < 0 || row >= n_local) return;
   const int deg = rowptr[row + 1] - rowptr[row];
   // only ~3B rows: parallelism is scarce, so no row shares a warp and rows above 4 warp-iterations get a CTA
   const int cls = deg >= 128 ? 0 : 1;
@@ -138,7 +144,6 @@ __global__ void __launch_bounds__(256) build_batch_rows_kernel(const int32_t* ba
   if (lane == leader) base = atomicAdd(counters + cls, __popc(mine));
   base = __shfl_sync(mine, base, leader);
   rows[cls * 3 * cap + base + __popc(mine & ((1u << lane) - 1))] = row;
-  atomicOr(row_mask + (row >> 5), 1u << (row & 31));
 }
 
 __global__ void finalize_losses_kernel(const float* bpr_losses, const float* nce_losses, int n_nce, float cl_rate, float* out) {
@@ -336,7 +341,8 @@ extern "C" int srb_train_step(const srb_step_desc* s, void* stream) {
   // ---- forward ----
   if (s->model != SRB_MODEL_MF) {
     SRB_TRY(check_cuda(cudaMemsetAsync(w.n_hub, 0, 16 + (size_t)((U + s->n_items + 31) / 32) * 4, st), "row mask memset"));
-    build_batch_rows_kernel<<<(3 * B + 255) / 256, 256, 0, st>>>(s->batch, B, U, s->adj.rowptr, w.batch_rows, w.n_hub, w.row_mask);
+    build_batch_rows_kernel<<<(3 * B + 255) / 256, 256, 0, st>>>(s->batch, B, U, s->adj.rowptr, 0, U + s->n_items, w.batch_rows, w.n_hub,
+                                                                   w.row_mask);
     SRB_TRY(post_launch("build_batch_rows_kernel"));
   }
   const float* table = s->params;  // table BPR gathers from
@@ -498,4 +504,18 @@ extern "C" int srb_train_step(const srb_step_desc* s, void* stream) {
     f.s[6] = seg(g2b, uq_i, ni_dev, B, U, cm);
   }
   return run_chain(s, w, c, &gd_live, true, st);
+}
+
+extern "C" int srb_build_batch_rows(const int32_t* batch, int32_t batch_cap, int32_t n_users, const int32_t* rowptr, int32_t row_begin,
+                                    int32_t n_local_rows, int32_t n_total_rows, int32_t* rows, int32_t* counters, uint32_t* row_mask,
+                                    void* stream) {
+  SRB_REQUIRE(batch && rowptr && rows && counters, "build_batch_rows: null pointer");
+  SRB_REQUIRE(batch_cap > 0 && row_begin >= 0 && n_local_rows >= 0 && row_begin + n_local_rows <= n_total_rows,
+              "build_batch_rows: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  SRB_TRY(srb::check_cuda(cudaMemsetAsync(counters, 0, 16, st), "batch rows memset"));
+  if (row_mask) SRB_TRY(srb::check_cuda(cudaMemsetAsync(row_mask, 0, (size_t)((n_total_rows + 31) / 32) * 4, st), "row mask memset"));
+  srb::build_batch_rows_kernel<<<(3 * batch_cap + 255) / 256, 256, 0, st>>>(batch, batch_cap, n_users, rowptr, row_begin, n_local_rows,
+                                                                           rows, counters, row_mask);
+  return srb::post_launch("build_batch_rows_kernel");
 }

@@ -401,7 +401,8 @@ extern "C" int srb_spmm_csr(const srb_spmm_desc* desc, void* stream) {
 extern "C" int srb_spmm_csr_allgather(const srb_spmm_sharded_desc* desc, void* stream) {
   SRB_REQUIRE(desc != nullptr, "spmm_allgather: null desc");
   SRB_REQUIRE(desc->world >= 1 && desc->world <= 8, "spmm_allgather: world must be 1..8");
-  SRB_REQUIRE(desc->row_begin >= 0 && desc->row_begin + desc->local.n_rows <= desc->local.n_cols,
+  // (with a device-classified row list n_rows is the list capacity, not the number of owned rows)
+  SRB_REQUIRE(desc->row_begin >= 0 && (desc->local.n_vlong_dev || desc->row_begin + desc->local.n_rows <= desc->local.n_cols),
               "spmm_allgather: owned rows [%d, %d) outside [0, %d)", desc->row_begin, desc->row_begin + desc->local.n_rows,
               desc->local.n_cols);
   srb::SpmmArgs a;

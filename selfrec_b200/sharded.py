@@ -105,8 +105,9 @@ class ShardedPropagator:
         """Device-side barrier across ranks on the current stream (pushed rows become visible)."""
         self.handles[0].barrier(channel=0)
 
-    def spmm(self, x, push_y=None, push_sum=None, push_p=None, **epi):
-        """Own rows of A @ x with the fused pushes; x and all epilogue tensors are full [N, d]."""
+    def spmm(self, x, push_y=None, push_sum=None, push_p=None, row_list=None, **epi):
+        """Own rows of A @ x with the fused pushes; x and all epilogue tensors are full [N, d].
+        row_list = (rows, counters, capacity): only the listed local rows (srb_build_batch_rows)."""
         from . import ops
         torch = self.torch
         lib = _lib.load()
@@ -124,6 +125,11 @@ class ShardedPropagator:
                 setattr(loc, k, ops._p(v))
             else:
                 setattr(loc, k, v)
+        if row_list is not None:
+            rows, counters, cap = row_list
+            keep += [rows, counters]
+            loc.row_order, loc.n_rows, loc.n_long_rows, loc.n_vlong_rows = ops._p(rows), cap, 0, 0
+            loc.n_vlong_dev = ops._p(counters)
         sd.row_begin, sd.world = self.shard.row_begin, (1 if self.use_mc else self.world)
         for idx, field in ((push_y, "peer_Y"), (push_sum, "peer_sum"), (push_p, "peer_p")):
             if idx is not None:
@@ -143,10 +149,11 @@ class ShardedXSimGCL:
     (BPR, L2, InfoNCE over <= 3B + 2B gathered rows) are replicated on every rank from the gathered
     layers -- they touch ~2 MB and would cost more to distribute than to recompute.  All ranks hold
     bit-identical parameters after every step because every rank consumes the same pushed rows.
-    Buffers (symmetric): 0 params, 1/2 layer ping-pong, 3 cl view, 4 final, 5/6 backward ping-pong.
+    Buffers (symmetric): 0 params, 1/2 layer ping-pong, 3 cl view, 4 final (running layer sum), 5/6 backward
+    ping-pong, 7 batch rows of the final mean (training steps evaluate the last layer on the batch rows only).
     """
 
-    P, W0, W1, CL, FIN, A0, A1 = range(7)
+    P, W0, W1, CL, FIN, A0, A1, FINB = range(8)
 
     def __init__(self, model, data, emb_size, n_layers, batch_size, lr, reg, *, eps=0.0, tau=0.2, cl_rate=0.0, layer_cl=0,
                  l2_div=1.0, init_user=None, init_item=None, group=None):
@@ -156,7 +163,7 @@ class ShardedXSimGCL:
             raise _lib.SrbError("sharded engine covers XSimGCL and LightGCN")
         self.torch, self.ops = torch, ops
         self.model = model
-        self.prop = ShardedPropagator(data.norm_adj, emb_size, 7, group)
+        self.prop = ShardedPropagator(data.norm_adj, emb_size, 8, group)
         p = self.prop
         self.U, self.I, self.d, self.L, self.B = int(data.user_num), int(data.item_num), int(emb_size), int(n_layers), int(batch_size)
         self.N = self.U + self.I
@@ -185,7 +192,7 @@ class ShardedXSimGCL:
     def set_noise_tensor(self, noise):
         self.noise = self.ops._f32c(noise, "noise")  # [1, L, N, d]
 
-    def _forward(self, perturbed, philox_seed=0x5EED):
+    def _forward(self, perturbed, philox_seed=0x5EED, batch_rows_only=False):
         p, ops = self.prop, self.ops
         L = self.L
         ego = self.model == "LightGCN"
@@ -208,7 +215,12 @@ class ShardedXSimGCL:
                 else:
                     epi.update(noise_mode=2, philox_seed=philox_seed, philox_offset=0x10 + k, philox_step_dev=self.step_dev)
             # the running sum only needs to travel once it is final
-            p.spmm(x, push_y=ybuf, push_sum=self.FIN if last else None, **epi)
+            if last and batch_rows_only:
+                # out of place (the list may hold a row twice): final rows go to FINB on every rank
+                epi["sum_out"] = p.bufs[self.FINB]
+                p.spmm(x, push_y=ybuf, push_sum=self.FINB, row_list=(self._brows, self._bcnt, 3 * self.B), **epi)
+            else:
+                p.spmm(x, push_y=ybuf, push_sum=self.FIN if last else None, **epi)
             p.barrier()
             if ybuf is not None:
                 x = p.bufs[ybuf]
@@ -236,7 +248,13 @@ class ShardedXSimGCL:
         self._bl = torch.zeros(2, device=dev)
         self._nl = torch.zeros(2, device=dev)
         self._gn = [torch.zeros((B, d), device=dev) for _ in range(4)]  # g1 / g2 of the user and item problems
-        fin, cl = p.bufs[self.FIN], p.bufs[self.CL]
+        # batch rows of this rank's block by degree class + bitmap of all batch rows (srb_build_batch_rows)
+        self._brows = torch.zeros(9 * B, dtype=torch.int32, device=dev)
+        self._bcnt = torch.zeros(4, dtype=torch.int32, device=dev)
+        self._rmask = torch.zeros((self.N + 31) // 32, dtype=torch.int32, device=dev)
+        # the final mean is only read at the batch rows: unless the last layer is the CL view, it is evaluated there only
+        self._subset = not (self.model == "XSimGCL" and self.layer_cl == self.L) and self.L >= 1
+        fin, cl = p.bufs[self.FINB if self._subset else self.FIN], p.bufs[self.CL]
         u_idx, i_idx, j_idx, uq_u, uq_i = self._idx
         bd = _lib.BprDesc()
         bd.emb, bd.n_users, bd.d = ops._p(fin), U, d
@@ -291,7 +309,11 @@ class ShardedXSimGCL:
         lib = _lib.load()
         L = self.L
         ops.adam_prepare(self.step_dev, self.scalars, self.lr)
-        self._forward(True)
+        sh = p.shard
+        _lib.check(lib.srb_build_batch_rows(ops._p(self.batch_dev), self.B, self.U, ops._p(p.rowptr), sh.row_begin, sh.n_rows, self.N,
+                                            ops._p(self._brows), ops._p(self._bcnt), ops._p(self._rmask), ops._stream()),
+                   "srb_build_batch_rows")
+        self._forward(True, batch_rows_only=self._subset)
         # ---- replicated batch losses on the gathered layers ----
         _lib.check(lib.srb_bpr_l2_fwd_bwd(C.byref(self._bpr_desc), ops._stream()), "srb_bpr_l2_fwd_bwd")
         if self._nce_desc is not None:
@@ -304,7 +326,8 @@ class ShardedXSimGCL:
         x_idx = self.A0
         for k in range(L - 1, 0, -1):
             y_idx = self.A1 if x_idx == self.A0 else self.A0
-            p.spmm(p.bufs[x_idx], push_y=y_idx)
+            # the seed of the chain is non-zero at the batch rows only: the first product skips every other column
+            p.spmm(p.bufs[x_idx], push_y=y_idx, **(dict(col_mask=self._rmask) if k == L - 1 else {}))
             p.barrier()
             # replicated: every rank adds the same sparse rows to its copy
             ops.scatter_add_segments(p.bufs[y_idx], final_segs + (cl_segs if self.layer_cl == k else []))
@@ -317,6 +340,8 @@ class ShardedXSimGCL:
         epi = dict(adam_p=p.bufs[self.P], adam_m=self.m, adam_v=self.v, adam_scalars=self.scalars, beta1=0.9, beta2=0.999, adam_eps=1e-8)
         if extra is not None:
             epi["extra"] = extra
+        if L == 1:
+            epi["col_mask"] = self._rmask
         p.spmm(p.bufs[x_idx], push_p=self.P, **epi)
         p.barrier()
         ls = self.losses
