@@ -20,7 +20,7 @@ def coo_adj(csr):
     coo = csr.tocoo()
     i = torch.from_numpy(np.vstack([coo.row, coo.col]).astype(np.int64))
     v = torch.from_numpy(coo.data.astype(np.float32))
-    return torch.sparse_coo_tensor(i, v, coo.shape)
+    return torch.sparse_coo_tensor(i, v, coo.shape, check_invariants=False)
 
 
 def bpr_loss(u, p, n):  # util/loss_torch.py:6-10
