@@ -1,78 +1,67 @@
 """Lifecycle base class with the attribute surface of base/recommender.py:7-83.
 
-Only what GraphRecommender and the in-scope models rely on: config unpacking, the
+Only what GraphRecommender and the in-scope models rely on: config unpacking (table-driven here), the
 build -> train -> test -> evaluate template, and the log handle."""
-from os.path import abspath
-from time import localtime, strftime, time
+import os
+import time
 
 from ..data.data import Data
 from ..util.logger import Log
+
+# attribute, YAML key, conversion, label printed by print_model_info (None: not printed)
+_SETTINGS = (
+    ("ranking", "item.ranking.topN", lambda v: v, None),
+    ("emb_size", "embedding.size", int, "Embedding Dimension:"),
+    ("maxEpoch", "max.epoch", int, "Maximum Epoch:"),
+    ("lRate", "learning.rate", float, "Learning Rate:"),
+    ("batch_size", "batch.size", int, "Batch Size:"),
+    ("reg", "reg.lambda", float, "Regularization Parameter:"),
+    ("output", "output", lambda v: v, None),
+)
+_STAGES = (("Initializing and building model...", "build"), ("Training Model...", "train"))
+
+
+def _noop(self, *args, **kwargs):
+    return None
 
 
 class Recommender:
     def __init__(self, conf, training_set, test_set, **kwargs):
         self.config = conf
-        self.data = Data(self.config, training_set, test_set)
-        model_config = self.config["model"]
-        self.model_name = model_config["name"]
-        self.ranking = self.config["item.ranking.topN"]
-        self.emb_size = int(self.config["embedding.size"])
-        self.maxEpoch = int(self.config["max.epoch"])
-        self.batch_size = int(self.config["batch.size"])
-        self.lRate = float(self.config["learning.rate"])
-        self.reg = float(self.config["reg.lambda"])
-        self.output = self.config["output"]
-        stamp = strftime("%Y-%m-%d %H-%M-%S", localtime(time()))
-        self.model_log = Log(self.model_name, f"{self.model_name} {stamp}")
-        self.result = []
-        self.recOutput = []
+        self.data = Data(conf, training_set, test_set)
+        self.model_name = conf["model"]["name"]
+        for attr, key, cast, _label in _SETTINGS:
+            setattr(self, attr, cast(conf[key]))
+        now = time.strftime("%Y-%m-%d %H-%M-%S", time.localtime(time.time()))
+        self.model_log = Log(self.model_name, self.model_name + " " + now)
+        self.result, self.recOutput = [], []
 
     def initializing_log(self):
-        self.model_log.add("### model configuration ###")
-        for k, v in self.config.config.items():
-            self.model_log.add(f"{k}={v}")
+        log = self.model_log.add
+        log("### model configuration ###")
+        for key, value in self.config.config.items():
+            log(f"{key}={value}")
 
     def print_model_info(self):
-        print("Model:", self.model_name)
-        print("Training Set:", abspath(self.config["training.set"]))
-        print("Test Set:", abspath(self.config["test.set"]))
-        print("Embedding Dimension:", self.emb_size)
-        print("Maximum Epoch:", self.maxEpoch)
-        print("Learning Rate:", self.lRate)
-        print("Batch Size:", self.batch_size)
-        print("Regularization Parameter:", self.reg)
-        if self.config.contain(self.model_name):
-            args = self.config[self.model_name]
-            print("Specific parameters:", "  ".join(f"{k}:{args[k]}" for k in args))
+        conf = self.config
+        rows = [("Model:", self.model_name)]
+        rows += [(label, os.path.abspath(conf[key])) for label, key in (("Training Set:", "training.set"), ("Test Set:", "test.set"))]
+        rows += [(label, getattr(self, attr)) for attr, _key, _cast, label in _SETTINGS if label]
+        for label, value in rows:
+            print(label, value)
+        if conf.contain(self.model_name):
+            extra = conf[self.model_name]
+            print("Specific parameters:", "  ".join(f"{k}:{extra[k]}" for k in extra))
 
-    def build(self):
-        pass
-
-    def train(self):
-        pass
-
-    def predict(self, u):
-        pass
-
-    def test(self):
-        pass
-
-    def save(self):
-        pass
-
-    def load(self):
-        pass
-
-    def evaluate(self, rec_list):
-        pass
+    # hooks the concrete models fill in
+    build = train = predict = test = save = load = evaluate = _noop
 
     def execute(self):
         self.initializing_log()
         self.print_model_info()
-        print("Initializing and building model...")
-        self.build()
-        print("Training Model...")
-        self.train()
+        for banner, stage in _STAGES:
+            print(banner)
+            getattr(self, stage)()
         print("Testing...")
         rec_list = self.test()
         print("Evaluating...")

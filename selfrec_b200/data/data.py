@@ -1,7 +1,6 @@
-class Data(object):
-    """Mirror of data/data.py: holds the config and the raw train/test triples."""
+"""Base of Interaction (data/data.py): the run's configuration plus the raw training / test triples."""
 
+
+class Data(object):
     def __init__(self, conf, training, test):
-        self.config = conf
-        self.training_data = training
-        self.test_data = test
+        self.config, self.training_data, self.test_data = conf, training, test
