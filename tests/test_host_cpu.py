@@ -350,6 +350,24 @@ def test_ctypes_structs_match_the_header_layout(tmp_path):
             assert int(out[f"{cname}.{fname}"]) == getattr(st, fname).offset, f"{cname}.{fname}"
 
 
+def test_graph_augmentor_matches_reference_drops(built_lib, golden):
+    """R11: node_dropout / edge_dropout against what the unmodified reference dropped for the same `random`
+    seed (oracle/gen_golden_augment.py), including where the generator stands afterwards."""
+    from selfrec_b200.data.augmentor import GraphAugmentor
+    fx = golden("augment.npz")
+    shape = tuple(int(x) for x in fx["in_shape"])
+    mat = sp.csr_matrix((np.ones(len(fx["in_indices"]), np.float32), fx["in_indices"], fx["in_indptr"]), shape=shape)
+    for case in fx["cases"]:
+        kind, rate, seed, tag = str(case).split(":")
+        random.seed(int(seed))
+        got = sp.csr_matrix(getattr(GraphAugmentor, kind)(mat, float(rate)))
+        got.sum_duplicates()
+        got.eliminate_zeros()
+        want = sp.csr_matrix((fx[tag + "_data"], fx[tag + "_indices"], fx[tag + "_indptr"]), shape=shape)
+        assert _same_csr(got, want), case
+        assert random.random() == float(fx[tag + "_next_random"][0]), case
+
+
 def test_install_aliases_boundary_modules(built_lib):
     import sys
     import selfrec_b200
