@@ -116,12 +116,19 @@ def test_normalize_isolated_nodes_and_rectangular():
     assert np.allclose(Graph.normalize_graph_mat(r).toarray(), [[0.5, 0.5, 0, 0], [0, 0, 0, 0]])
 
 
-def test_native_sampler_bit_exact_with_reference(built_lib, golden, tiny_triples, tiny_conf, in_tmp_cwd):
+@pytest.mark.parametrize("route", ["python_lists", "native_builder"])
+def test_native_sampler_bit_exact_with_reference(built_lib, golden, tiny_triples, tiny_conf, in_tmp_cwd, route):
+    from selfrec_b200.data.loader import FileIO
     from selfrec_b200.data.ui_graph import Interaction
     from selfrec_b200.util.sampler import next_batch_pairwise
     train, test = tiny_triples
     s = golden("sampler.npz")
-    d = Interaction(tiny_conf("MF"), [list(t) for t in train], [list(t) for t in test])
+    if route == "python_lists":
+        d = Interaction(tiny_conf("MF"), [list(t) for t in train], [list(t) for t in test])
+    else:  # the object the native dataset builder returns must drive the sampler identically
+        d = Interaction(tiny_conf("MF"), FileIO.load_data_set(os.path.join(GOLDEN, "tiny_train.txt")),
+                        FileIO.load_data_set(os.path.join(GOLDEN, "tiny_test.txt")))
+        assert type(d) is not Interaction
     random.seed(int(s["seed"]))
     for epoch in range(2):
         us, is_, js = [], [], []
