@@ -284,7 +284,8 @@ typedef struct srb_topk_desc {
   int32_t k;
   int32_t* out_ids;
   float* out_scores;
-  int32_t impl; /* 0 auto, 1 cuda-core fp32, 2 tcgen05 3xTF32 + exact rescoring */
+  int32_t impl; /* 0 auto; 1 CUDA cores, exact fp32; 2 tcgen05 TF32 candidate lists (2 x 24 per user) + exact fp32
+                   rescoring + a per-user exactness certificate, uncertified users re-run by the exact path */
   void* workspace; /* impl 2: srb_topk_workspace_bytes */
   int64_t workspace_bytes;
 } srb_topk_desc;
@@ -293,12 +294,12 @@ int64_t srb_topk_workspace_bytes(int32_t n_q, int32_t n_items, int32_t d, int32_
 /* byte offset (inside the impl-2 workspace) of the int32 count of users the exact fallback re-ran */
 int64_t srb_topk_fallback_count_offset(int32_t n_q, int32_t n_items);
 int srb_score_topk(const srb_topk_desc* desc, void* stream);
-/* Mask-free top-k of precomputed score rows [n_q, n_items] (models whose predict() is not one
- * dot product, e.g. BUIR.py); same selection rule.  The caller applies the -10e8 mask. */
 /* Dense score rows out[q, i] = <user_emb[users[q]], item_emb[i]>, the reference's predict()
  * (XSimGCL.py:57-60); same fp32 fma chain as srb_score_topk. */
 int srb_score_rows(const float* user_emb, const float* item_emb, int32_t d, const int32_t* users,
                    int32_t n_q, int32_t n_items, float* out, void* stream);
+/* Mask-free top-k of precomputed score rows [n_q, n_items] (models whose predict() is not one
+ * dot product, e.g. BUIR.py); same selection rule.  The caller applies the -10e8 mask. */
 int srb_topk_rows(const float* scores, int32_t n_q, int32_t n_items, int32_t k, int32_t* out_ids,
                   float* out_scores, void* stream);
 
