@@ -1,0 +1,93 @@
+"""CPU models of the two numerical arguments the tensor-core kernels rest on (numpy only, no GPU):
+
+* 3xTF32 (csrc/infonce_tc.cuh): x = hi + lo with hi = rna_tf32(x), lo truncated to TF32; hi*hi + hi*lo + lo*hi
+  reproduces an fp32 dot product to ~2^-21 relative, a single TF32 pass only to ~2^-11.
+* the exactness certificate of the tcgen05 ranking path (csrc/score_topk_tc.cu): with TF32-truncated operands
+  every approximate score is within E = (2^-9 + 2^-16 + 2^-18) * ||u|| * max||i|| of the exact one, so if the best
+  non-candidate bound max(thr_A, thr_B) + E is below the exact k-th score, the true top-k lies inside the
+  2 x 24 candidates -- whatever the data.
+"""
+import numpy as np
+import pytest
+
+
+def tf32_trunc(x):
+    b = np.asarray(x, dtype=np.float32).view(np.uint32) & np.uint32(0xFFFFE000)
+    return b.view(np.float32)
+
+
+def tf32_rna(x):
+    """cvt.rna.tf32.f32: round to nearest, ties away from zero, 10 explicit mantissa bits."""
+    b = np.asarray(x, dtype=np.float32).view(np.uint32)
+    return ((b + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+def test_3xtf32_split_error_model():
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((256, 64)).astype(np.float32)
+    b = rng.standard_normal((256, 64)).astype(np.float32)
+    exact = a.astype(np.float64) @ b.astype(np.float64).T
+    scale = np.linalg.norm(a, axis=1)[:, None] * np.linalg.norm(b, axis=1)[None, :]
+    one = tf32_trunc(a).astype(np.float64) @ tf32_trunc(b).astype(np.float64).T
+    ah, bh = tf32_rna(a), tf32_rna(b)
+    al, bl = tf32_trunc(a - ah), tf32_trunc(b - bh)  # the tensor core truncates the low parts
+    f = lambda x: x.astype(np.float64)
+    three = f(ah) @ f(bh).T + f(ah) @ f(bl).T + f(al) @ f(bh).T
+    e1 = np.abs(one - exact).max() / scale.max()
+    e3 = np.abs(three - exact).max() / scale.max()
+    assert e3 < 2.0 ** -20 and e1 > 50 * e3  # the split buys ~3 decimal digits
+    assert np.abs(one - exact).max() <= (2.0 ** -9) * scale.max()
+
+
+def _certified_topk(U, I, k, rated):
+    """numpy model of tc_score_kernel + tc_rescore_kernel for one block of users; returns (ids or None per user)."""
+    n_u, n_i = U.shape[0], I.shape[0]
+    approx = (tf32_trunc(U).astype(np.float64) @ tf32_trunc(I).astype(np.float64).T).astype(np.float32)
+    exact = U.astype(np.float64) @ I.astype(np.float64).T
+    bmax = np.linalg.norm(I.astype(np.float64), axis=1).max()
+    col_half = (np.arange(n_i) // 64) % 2  # 128-item tiles, two 64-column halves
+    out = []
+    for q in range(n_u):
+        ok = np.ones(n_i, bool)
+        ok[rated[q]] = False
+        cand, thr = [], -np.inf
+        for h in (0, 1):
+            cols = np.flatnonzero(ok & (col_half == h))
+            order = cols[np.argsort(-approx[q, cols], kind="stable")]
+            cand += list(order[:24])
+            if len(order) > 24:
+                thr = max(thr, float(approx[q, order[23]]))  # everything not kept in this half is <= its 24th best
+        cand = np.array(cand, dtype=np.int64)
+        if len(cand) < k:
+            out.append(None)
+            continue
+        top = cand[np.argsort(-exact[q, cand], kind="stable")][:k]
+        kth = exact[q, top[-1]]
+        E = (2.0 ** -9 + 2.0 ** -16 + 2.0 ** -18) * np.linalg.norm(U[q].astype(np.float64)) * bmax
+        out.append(top if thr + E < kth else None)  # None = handed to the exact fallback
+    return out, exact
+
+
+@pytest.mark.parametrize("spread", [1.0, 1e-2, 1e-4])
+def test_ranking_certificate_is_sound(spread):
+    """Whenever the certificate passes, the candidates contain the exact top-k -- also when scores are packed
+    so tightly that TF32 cannot tell them apart (then users fail the certificate instead of returning wrong ids)."""
+    rng = np.random.default_rng(int(1 / spread))
+    n_u, n_i, d, k = 48, 1500, 64, 20
+    base = rng.standard_normal(d).astype(np.float32)
+    U = (base + spread * rng.standard_normal((n_u, d))).astype(np.float32)
+    I = (base + spread * rng.standard_normal((n_i, d))).astype(np.float32)
+    rated = [rng.choice(n_i, size=rng.integers(0, 40), replace=False) for _ in range(n_u)]
+    got, exact = _certified_topk(U, I, k, rated)
+    certified = 0
+    for q, ids in enumerate(got):
+        if ids is None:
+            continue
+        certified += 1
+        ok = np.ones(n_i, bool)
+        ok[rated[q]] = False
+        cols = np.flatnonzero(ok)
+        truth = cols[np.argsort(-exact[q, cols], kind="stable")][:k]
+        assert set(ids.tolist()) == set(truth.tolist()), (spread, q)
+    if spread == 1.0:
+        assert certified == n_u  # well-separated scores: nobody needs the fallback
