@@ -91,3 +91,25 @@ def test_ranking_certificate_is_sound(spread):
         assert set(ids.tolist()) == set(truth.tolist()), (spread, q)
     if spread == 1.0:
         assert certified == n_u  # well-separated scores: nobody needs the fallback
+
+
+@pytest.mark.parametrize("tau", [0.5, 0.2, 0.05, 0.025])
+def test_fixed_shift_logsumexp_model(tau):
+    """InfoNCE pass A (csrc/infonce_tc.cuh) shifts every logit by the bound 1/tau of a cosine logit instead of a
+    running maximum, which makes column-split partial sums plainly additive.  fp32 model: the result equals the
+    max-shifted log-sum-exp to fp32 rounding for every temperature the tensor-core path accepts (tau >= 0.025)."""
+    rng = np.random.default_rng(7)
+    n, d = 512, 64
+    v1 = rng.standard_normal((n, d))
+    v2 = v1 + 0.3 * rng.standard_normal((n, d))
+    v1 /= np.linalg.norm(v1, axis=1, keepdims=True)
+    v2 /= np.linalg.norm(v2, axis=1, keepdims=True)
+    S = (v1 @ v2.T / tau)
+    ref = np.log(np.exp(S - S.max(1, keepdims=True)).sum(1)) + S.max(1)
+    S32 = S.astype(np.float32)
+    shift = np.float32(1.0 / tau)
+    parts = [np.exp(S32[:, c::4] - shift, dtype=np.float32).sum(1, dtype=np.float32) for c in range(4)]  # 4 column splits
+    l = parts[0] + parts[1] + parts[2] + parts[3]
+    got = shift + np.log(l, dtype=np.float32)
+    assert np.isfinite(got).all() and (l > 0).all()
+    assert np.abs(got - ref).max() <= 4e-7 / tau + 1e-6
