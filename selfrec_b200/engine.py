@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import _lib, ops
-from .util.sampler import NativePairSampler
+from .util.sampler import NativePairSampler, permute_training_data
 
 
 class LossHandle:
@@ -178,8 +178,7 @@ class TrainEngine:
         s = self.sampler
         s.pull_state()
         perm = s.begin_epoch(want_perm=True)
-        td = self.data.training_data
-        td[:] = [td[k] for k in perm]
+        permute_training_data(self.data, perm)
         if exact_lazy:
             s.push_state()
             buf = np.empty(self.words, dtype=np.int32)

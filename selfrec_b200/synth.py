@@ -8,6 +8,7 @@ power-law graph with the same shape as the named configuration (yelp2018: 31 668
 import numpy as np
 import scipy.sparse as sp
 
+from .data.data import Data
 from .data.graph import Graph
 
 SHAPES = {
@@ -66,7 +67,7 @@ def make_pairs(n_users, n_items, nnz, seed=0, alpha_u=0.42, alpha_i=0.40):
     return _first_appearance_relabel(u, n_users).astype(np.int32), _first_appearance_relabel(i, n_items).astype(np.int32)
 
 
-class ArrayInteraction(Graph):
+class ArrayInteraction(Data, Graph):
     """The subset of data/ui_graph.py's Interaction the CUDA path consumes, built straight
     from id arrays (no name dictionaries).  training_data holds (user_id, item_id, 1.0)."""
 
@@ -74,7 +75,7 @@ class ArrayInteraction(Graph):
         self.pair_users = np.ascontiguousarray(pair_users, dtype=np.int32)
         self.pair_items = np.ascontiguousarray(pair_items, dtype=np.int32)
         self.user_num, self.item_num = int(n_users), int(n_items)
-        self.training_data = list(zip(self.pair_users.tolist(), self.pair_items.tolist()))
+        Data.__init__(self, None, list(zip(self.pair_users.tolist(), self.pair_items.tolist())), [])
         n = self.user_num + self.item_num
         ones = np.ones(len(self.pair_users), dtype=np.float32)
         half = sp.csr_matrix((ones, (self.pair_users, self.pair_items.astype(np.int64) + self.user_num)), shape=(n, n), dtype=np.float32)

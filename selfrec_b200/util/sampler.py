@@ -76,10 +76,20 @@ class NativePairSampler:
 
 def _sampler_for(data):
     s = getattr(data, "_srb_sampler", None)
-    if s is None or s.n_pairs != len(data.training_data):
+    n = len(data.pair_users) if hasattr(data, "pair_users") else len(data.training_data)
+    if s is None or s.n_pairs != n:
         s = NativePairSampler(data)
         data._srb_sampler = s
     return s
+
+
+def permute_training_data(data, perm):
+    """data.training_data[k] <- data.training_data[perm[k]], lazily when the data object supports it."""
+    if hasattr(data, "shuffle_training_data"):
+        data.shuffle_training_data(perm)
+    else:
+        td = data.training_data
+        td[:] = [td[k] for k in perm]
 
 
 def next_batch_pairwise(data, batch_size, n_negs=1):
@@ -87,8 +97,7 @@ def next_batch_pairwise(data, batch_size, n_negs=1):
     s.pull_state()
     perm = s.begin_epoch(want_perm=True)
     s.push_state()
-    td = data.training_data
-    td[:] = [td[k] for k in perm]  # the in-place shuffle side effect (sampler.py:7)
+    permute_training_data(data, perm)  # the in-place shuffle side effect (sampler.py:7)
     u = np.empty(batch_size, dtype=np.int32)
     i = np.empty(batch_size, dtype=np.int32)
     j = np.empty(batch_size * n_negs, dtype=np.int32)

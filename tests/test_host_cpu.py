@@ -375,6 +375,29 @@ def test_graph_augmentor_matches_reference_drops(built_lib, golden):
         assert random.random() == float(fx[tag + "_next_random"][0]), case
 
 
+def test_lazy_training_data_shuffles_compose(built_lib):
+    """The sampler records its epoch shuffles as a pending permutation; reading data.training_data applies them
+    to the same list object, in order (util/sampler.py:7 shuffles that list in place every epoch)."""
+    from selfrec_b200 import synth
+    from selfrec_b200.data.native import load_interaction
+    rng = np.random.default_rng(0)
+    d = synth.make_interaction((50, 60, 400), seed=0)
+    objs = [d, load_interaction(None, os.path.join(GOLDEN, "tiny_train.txt"))]
+    for obj in objs:
+        n = len(obj.pair_users)
+        first = list(obj.training_data) if obj is d else None  # the native object builds its list on first access
+        p1, p2 = rng.permutation(n), rng.permutation(n)
+        obj.shuffle_training_data(p1)
+        obj.shuffle_training_data(p2)
+        got = obj.training_data
+        if first is None:
+            un, inn = obj._unames, obj._inames
+            first = [[un[u], inn[i], w] for u, i, w in zip(obj.pair_users.tolist(), obj.pair_items.tolist(), obj.pair_weights.tolist())]
+        want = [first[k] for k in p1]
+        want = [want[k] for k in p2]
+        assert got == want and obj.training_data is got  # applied once, same list afterwards
+
+
 def test_install_aliases_boundary_modules(built_lib):
     import sys
     import selfrec_b200
