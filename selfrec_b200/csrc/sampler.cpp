@@ -31,6 +31,7 @@ struct srb_sampler {
   int32_t n_users, n_items;
   int64_t ptr;
   bool epoch_open;
+  std::vector<uint64_t> ubits, ibits;  // scratch bitmaps of sorted_unique
 
   inline uint32_t genrand() {
     static const uint32_t mag01[2] = {0x0u, 0x9908b0dfu};
@@ -174,10 +175,28 @@ extern "C" int srb_sampler_begin_epoch(srb_sampler* s, int64_t* perm_out) {
   return SRB_OK;
 }
 
-static int sorted_unique(const int32_t* src, int n, int32_t* dst) {
-  memcpy(dst, src, (size_t)n * sizeof(int32_t));
-  std::sort(dst, dst + n);
-  return (int)(std::unique(dst, dst + n) - dst);
+// sorted unique ids of src (torch.unique, XSimGCL.py:46-47).  Ids are < `universe`: one pass marks a bitmap,
+// one pass over its words emits the ids in order -- no comparison sort on the per-batch path.
+static int sorted_unique(const int32_t* src, int n, int32_t* dst, std::vector<uint64_t>& bits, int32_t universe) {
+  const size_t words = ((size_t)universe + 63) / 64;
+  if (bits.size() < words) bits.assign(words, 0);
+  if ((size_t)n * 16 < words) {  // tiny batch over a huge id space: sorting is cheaper than scanning the bitmap
+    memcpy(dst, src, (size_t)n * sizeof(int32_t));
+    std::sort(dst, dst + n);
+    return (int)(std::unique(dst, dst + n) - dst);
+  }
+  for (int t = 0; t < n; ++t) bits[(size_t)src[t] >> 6] |= (uint64_t)1 << (src[t] & 63);
+  int m = 0;
+  for (size_t w = 0; w < words; ++w) {
+    uint64_t b = bits[w];
+    if (!b) continue;
+    bits[w] = 0;  // leave the bitmap clean for the next call
+    while (b) {
+      dst[m++] = (int32_t)(w * 64 + (size_t)__builtin_ctzll(b));
+      b &= b - 1;
+    }
+  }
+  return m;
 }
 
 extern "C" int srb_sampler_next_batch(srb_sampler* s, int32_t batch_size, int32_t batch_cap, int32_t* out) {
@@ -202,6 +221,9 @@ extern "C" int srb_sampler_next_batch(srb_sampler* s, int32_t batch_size, int32_
   int32_t* uu = j + batch_cap;
   int32_t* ui = uu + batch_cap;
   for (int t = 0; t < b; ++t) {
+    // the rated list of a user is a random place in memory: fetch the ones a few positives ahead
+    if (t + 16 < b) __builtin_prefetch(&s->rated_ptr[s->pu[s->ptr + t + 16]]);
+    if (t + 8 < b) __builtin_prefetch(&s->rated_idx[(size_t)s->rated_ptr[s->pu[s->ptr + t + 8]]]);
     const int32_t user = s->pu[s->ptr + t];
     u[t] = user;
     i[t] = s->pi[s->ptr + t];
@@ -214,8 +236,8 @@ extern "C" int srb_sampler_next_batch(srb_sampler* s, int32_t batch_size, int32_
     j[t] = neg;
   }
   for (int t = b; t < batch_cap; ++t) u[t] = i[t] = j[t] = 0;
-  const int nu = sorted_unique(u, b, uu);
-  const int ni = sorted_unique(i, b, ui);
+  const int nu = sorted_unique(u, b, uu, s->ubits, s->n_users);
+  const int ni = sorted_unique(i, b, ui, s->ibits, s->n_items);
   for (int t = nu; t < batch_cap; ++t) uu[t] = 0;
   for (int t = ni; t < batch_cap; ++t) ui[t] = 0;
   out[0] = b;

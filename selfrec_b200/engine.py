@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import _lib, ops
-from .util.sampler import NativePairSampler, permute_training_data
+from .util.sampler import NativePairSampler, permute_training_data, stream_epoch
 
 
 class LossHandle:
@@ -172,28 +172,27 @@ class TrainEngine:
         return g
 
     def batches(self, exact_lazy=False):
-        """One epoch of batch words from the native sampler (advances Python's `random`)."""
+        """One epoch of batch words from the native sampler (advances Python's `random`).  The yielded buffer is
+        reused: consume it (step() copies it into a pinned slot) before asking for the next one.  exact_lazy=True
+        hands Python's `random` state back after every batch, like the reference's generator would."""
         if self.sampler is None:
             self.sampler = NativePairSampler(self.data)
         s = self.sampler
+        if not exact_lazy:
+            yield from stream_epoch(s, self.data, self.B, self.B)
+            return
         s.pull_state()
         perm = s.begin_epoch(want_perm=True)
         permute_training_data(self.data, perm)
-        if exact_lazy:
+        s.push_state()
+        buf = np.empty(self.words, dtype=np.int32)
+        while True:
+            s.pull_state()
+            b = s.next_batch(self.B, self.B, buf)
             s.push_state()
-            buf = np.empty(self.words, dtype=np.int32)
-            while True:
-                s.pull_state()
-                b = s.next_batch(self.B, self.B, buf)
-                s.push_state()
-                if b == 0:
-                    return
-                yield buf
-        else:
-            allb = s.epoch(self.B, self.B)
-            s.push_state()
-            for k in range(allb.shape[0]):
-                yield allb[k]
+            if b == 0:
+                return
+            yield buf
 
     # ---- inference ---------------------------------------------------------------------
     def forward_clean(self):

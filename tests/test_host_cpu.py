@@ -375,6 +375,44 @@ def test_graph_augmentor_matches_reference_drops(built_lib, golden):
         assert random.random() == float(fx[tag + "_next_random"][0]), case
 
 
+def test_stream_epoch_equals_epoch_array(built_lib):
+    """The streaming generator TrainEngine.batches() uses yields exactly the batches of srb_sampler_epoch for the
+    same `random` state, leaves the same state behind (also when abandoned half way) and shuffles training_data."""
+    from selfrec_b200 import synth
+    from selfrec_b200.util.sampler import NativePairSampler, stream_epoch
+    d1 = synth.make_interaction((300, 400, 6000), seed=2)
+    d2 = synth.make_interaction((300, 400, 6000), seed=2)
+    s1, s2 = NativePairSampler(d1), NativePairSampler(d2)
+    for ep in range(2):
+        random.seed(77 + ep)
+        s1.pull_state()
+        perm = s1.begin_epoch(want_perm=True)
+        want = s1.epoch(128, 128)
+        s1.push_state()
+        st_want = random.getstate()
+        random.seed(77 + ep)
+        got = np.stack([w.copy() for w in stream_epoch(s2, d2, 128, 128)])
+        assert random.getstate() == st_want and np.array_equal(got, want)
+        first = list(d1.training_data)
+        d1.shuffle_training_data(perm)
+        assert d1.training_data == d2.training_data and d1.training_data != first
+    # closing the generator early hands the state back at that point of the stream
+    random.seed(5)
+    g = stream_epoch(s2, d2, 128, 128)
+    for _ in range(3):
+        next(g)
+    g.close()
+    after_three = random.getstate()
+    random.seed(5)
+    s1.pull_state()
+    s1.begin_epoch(want_perm=False)
+    buf = np.empty(4 + 5 * 128, dtype=np.int32)
+    for _ in range(3):
+        s1.next_batch(128, 128, buf)
+    s1.push_state()
+    assert random.getstate() == after_three
+
+
 def test_lazy_training_data_shuffles_compose(built_lib):
     """The sampler records its epoch shuffles as a pending permutation; reading data.training_data applies them
     to the same list object, in order (util/sampler.py:7 shuffles that list in place every epoch)."""
