@@ -11,9 +11,10 @@ A step  = one pass of the hot path over one batch: propagate (3 SpMM) -> gather 
           InfoNCE -> Horner backward (3 SpMM) -> Adam, on in-kernel Philox noise.
 value   = steps/s with the batch indices already resident in HBM (a device pool of pre-sampled
           batches), CUDA-graph replay, CUDA-event timing, max over ranks.
-e2e     = the same metric through the public API with HOST buffers, every step: native sampler ->
-          TrainEngine.step(words, fetch_loss=True) (pinned H2D copy of the batch, the step, D2H copy of
-          the losses); the host reads the loss of step t while step t+1 runs (the last one after the loop).
+e2e     = the same metric through the public API with HOST buffers, every step: one native sampler call
+          (negatives + unique lists of that batch, inside the timed region) -> TrainEngine.step(words,
+          fetch_loss=True) (pinned H2D copy of the batch, the step, D2H copy of the losses); the host samples
+          batch t+1 and reads the loss of step t while step t+1 runs (the last one after the loop).
 --impl reference times the reference's CPU PyTorch path (oracle/torch_port.py, the op-for-op
 port pinned against the reference) on the host cores; rank 0 only.
 """
