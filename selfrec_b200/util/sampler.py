@@ -78,8 +78,9 @@ def stream_epoch(sampler, data, batch_size, batch_cap):
     """One epoch of batch buffers (srb_sampler_next_batch layout), sampled one native call per batch into ONE
     reused int32 buffer (the consumer copies it, e.g. into a pinned slot): sampling batch t+1 overlaps the GPU step
     of batch t, and 41 KB stay cache-resident instead of a 25 MB epoch array being first-touched (0.2 vs 0.4 ms
-    per batch at yelp2018).  Python's `random` state is taken at the start and handed back when the epoch ends or
-    the generator is closed; data.training_data gets the epoch's shuffle."""
+    per batch at yelp2018).  (A producer thread sampling ahead was tried and dropped: the queue hand-offs under the
+    GIL cost more than the 0.2 ms they hide.)  Python's `random` state is taken at the start and handed back when
+    the epoch ends or the generator is closed; data.training_data gets the epoch's shuffle."""
     sampler.pull_state()
     try:
         perm = sampler.begin_epoch(want_perm=True)
