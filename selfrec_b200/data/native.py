@@ -12,6 +12,7 @@ import numpy as np
 import scipy.sparse as sp
 
 from .. import _lib
+from .data import _PendingShuffles
 from .graph import Graph
 from .ui_graph import Interaction
 
@@ -84,7 +85,7 @@ class NativeInteraction(Interaction):
         self.interaction_mat = sp.csr_matrix((rv, rc, rp), shape=(U, I))
         self._rated = (rp.copy(), rc.copy())  # already sorted and unique
         self._lazy = {}
-        self._td_perm = None
+        self._td_pending = _PendingShuffles()
 
     # ---- name-keyed members of the reference object, built when somebody asks ----------------
     def _lazy_get(self, key, build):
@@ -95,22 +96,21 @@ class NativeInteraction(Interaction):
     @property
     def training_data(self):
         rows = self._lazy.get("training_data")
+        order = self._td_pending.take()
         if rows is None:  # first access: build the list, already in its current (shuffled) order
             pu, pi, pw = self.pair_users, self.pair_items, self.pair_weights
-            if self._td_perm is not None:
-                pu, pi, pw = pu[self._td_perm], pi[self._td_perm], pw[self._td_perm]
-                self._td_perm = None
+            if order is not None:
+                pu, pi, pw = pu[order], pi[order], pw[order]
             un, inn = self._unames, self._inames
             rows = self._lazy["training_data"] = [[un[u], inn[i], w] for u, i, w in zip(pu.tolist(), pi.tolist(), pw.tolist())]
-        elif self._td_perm is not None:
-            order, self._td_perm = self._td_perm.tolist(), None
-            rows[:] = [rows[k] for k in order]
+        elif order is not None:
+            rows[:] = [rows[k] for k in order.tolist()]
         return rows
 
     @training_data.setter
     def training_data(self, v):
         self._lazy["training_data"] = v
-        self._td_perm = None
+        self._td_pending = _PendingShuffles()
 
     @property
     def test_data(self):

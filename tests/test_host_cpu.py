@@ -431,15 +431,16 @@ def test_lazy_training_data_shuffles_compose(built_lib):
     for obj in objs:
         n = len(obj.pair_users)
         first = list(obj.training_data) if obj is d else None  # the native object builds its list on first access
-        p1, p2 = rng.permutation(n), rng.permutation(n)
-        obj.shuffle_training_data(p1)
-        obj.shuffle_training_data(p2)
+        perms = [rng.permutation(n) for _ in range(11)]  # more than the fold-into-one threshold
+        for p in perms:
+            obj.shuffle_training_data(p)
         got = obj.training_data
         if first is None:
             un, inn = obj._unames, obj._inames
             first = [[un[u], inn[i], w] for u, i, w in zip(obj.pair_users.tolist(), obj.pair_items.tolist(), obj.pair_weights.tolist())]
-        want = [first[k] for k in p1]
-        want = [want[k] for k in p2]
+        want = first
+        for p in perms:
+            want = [want[k] for k in p]
         assert got == want and obj.training_data is got  # applied once, same list afterwards
 
 
