@@ -254,6 +254,10 @@ class ShardedXSimGCL:
         self._rmask = torch.zeros((self.N + 31) // 32, dtype=torch.int32, device=dev)
         # the final mean is only read at the batch rows: unless the last layer is the CL view, it is evaluated there only
         self._subset = not (self.model == "XSimGCL" and self.layer_cl == self.L) and self.L >= 1
+        # measured and parity-checked at 2 ranks (unicast pushes, +1 %); with the multicast pushes of >= 4 ranks the
+        # layer exchange is no longer what bounds the step, and the combination has not been run: keep the plain route
+        self._sparse_tricks = not p.use_mc
+        self._subset = self._subset and self._sparse_tricks
         fin, cl = p.bufs[self.FINB if self._subset else self.FIN], p.bufs[self.CL]
         u_idx, i_idx, j_idx, uq_u, uq_i = self._idx
         bd = _lib.BprDesc()
@@ -327,7 +331,7 @@ class ShardedXSimGCL:
         for k in range(L - 1, 0, -1):
             y_idx = self.A1 if x_idx == self.A0 else self.A0
             # the seed of the chain is non-zero at the batch rows only: the first product skips every other column
-            p.spmm(p.bufs[x_idx], push_y=y_idx, **(dict(col_mask=self._rmask) if k == L - 1 else {}))
+            p.spmm(p.bufs[x_idx], push_y=y_idx, **(dict(col_mask=self._rmask) if (k == L - 1 and self._sparse_tricks) else {}))
             p.barrier()
             # replicated: every rank adds the same sparse rows to its copy
             ops.scatter_add_segments(p.bufs[y_idx], final_segs + (cl_segs if self.layer_cl == k else []))
@@ -340,7 +344,7 @@ class ShardedXSimGCL:
         epi = dict(adam_p=p.bufs[self.P], adam_m=self.m, adam_v=self.v, adam_scalars=self.scalars, beta1=0.9, beta2=0.999, adam_eps=1e-8)
         if extra is not None:
             epi["extra"] = extra
-        if L == 1:
+        if L == 1 and self._sparse_tricks:
             epi["col_mask"] = self._rmask
         p.spmm(p.bufs[x_idx], push_p=self.P, **epi)
         p.barrier()
