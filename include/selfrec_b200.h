@@ -347,6 +347,13 @@ int srb_dataset_interaction_csr(const srb_dataset* d, int32_t* rowptr, int32_t* 
 int srb_dataset_adjacency_csr(const srb_dataset* d, const float* d_inv, int32_t* rowptr,
                               int32_t* colidx, float* vals, float* rowsum);
 
+/* The same adjacency for arbitrary (user, item) pairs with unit weights (duplicates summed): the CSR assembly of
+ * Interaction.convert_to_laplacian_mat (data/ui_graph.py:58-65) for SGL's dropped graphs.  colidx / vals have
+ * capacity 2 * n_pairs; *nnz_out receives the number of stored entries; rowsum is optional. */
+int srb_bipartite_adjacency_csr(const int32_t* users, const int32_t* items, int64_t n_pairs, int32_t n_users,
+                                int32_t n_items, int32_t* rowptr, int32_t* colidx, float* vals, float* rowsum,
+                                int64_t* nnz_out);
+
 /* ---------------------------------------------------------------------------------------
  * Ranking metrics, device part (util/evaluation.py:9-15 `hits`, :85-97 NDCG):
  * hit_mask[q] bit r = 1 iff topk_ids[q, r] is in the test set of users[q]  (r < k <= 64).

@@ -132,6 +132,7 @@ SYMBOLS = {
     "srb_dataset_pairs": (C.c_int, [VP, C.c_int32, VP, VP, VP]),
     "srb_dataset_interaction_csr": (C.c_int, [VP, VP, VP, VP]),
     "srb_dataset_adjacency_csr": (C.c_int, [VP, VP, VP, VP, VP, VP]),
+    "srb_bipartite_adjacency_csr": (C.c_int, [VP, VP, C.c_int64, C.c_int32, C.c_int32, VP, VP, VP, VP, VP]),
     "srb_adam_prepare": (C.c_int, [VP, VP, C.c_double, C.c_double, C.c_double, VP]),
     "srb_adam_step": (C.c_int, [VP, VP, VP, VP, C.c_int64, VP, C.c_double, C.c_double, C.c_float, VP]),
     "srb_topk_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),

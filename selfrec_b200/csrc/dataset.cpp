@@ -332,3 +332,47 @@ extern "C" int srb_dataset_adjacency_csr(const srb_dataset* d, const float* d_in
   }
   return SRB_OK;
 }
+
+// (U+I) x (U+I) bipartite adjacency of arbitrary (user, item) pairs with unit weights, duplicates summed,
+// rows = users then items, columns ascending: the CSR assembly of Interaction.convert_to_laplacian_mat
+// (data/ui_graph.py:58-65) for SGL's dropped graphs, without scipy's COO -> CSR -> transpose -> add chain.
+// Capacity of colidx / vals: 2 * n_pairs.  rowsum (optional) = fp32 row sums.  Returns the number of stored
+// entries in *nnz_out.
+extern "C" int srb_bipartite_adjacency_csr(const int32_t* users, const int32_t* items, int64_t n_pairs, int32_t n_users, int32_t n_items,
+                                           int32_t* rowptr, int32_t* colidx, float* vals, float* rowsum, int64_t* nnz_out) {
+  if ((n_pairs > 0 && (!users || !items)) || !rowptr || (n_pairs > 0 && (!colidx || !vals)) || !nnz_out || n_pairs < 0 || n_users < 0 ||
+      n_items < 0 || n_pairs > (int64_t)INT32_MAX / 2) {
+    srb::set_error("bipartite_adjacency_csr: bad arguments");
+    return SRB_ERR_ARG;
+  }
+  std::vector<int32_t> u(users, users + n_pairs), it(items, items + n_pairs);
+  for (int64_t k = 0; k < n_pairs; ++k)
+    if (u[(size_t)k] < 0 || u[(size_t)k] >= n_users || it[(size_t)k] < 0 || it[(size_t)k] >= n_items) {
+      srb::set_error("bipartite_adjacency_csr: pair %lld out of range", (long long)k);
+      return SRB_ERR_ARG;
+    }
+  std::vector<int32_t> r_ptr, r_col, t_ptr, t_col;
+  std::vector<float> r_val, t_val;
+  build_csr(n_users, u, it, r_ptr, r_col, r_val);
+  build_csr(n_items, it, u, t_ptr, t_col, t_val);
+  int64_t o = 0;
+  rowptr[0] = 0;
+  for (int r = 0; r < n_users + n_items; ++r) {
+    const bool is_user = r < n_users;
+    const int lr = is_user ? r : r - n_users;
+    const std::vector<int32_t>& ptr = is_user ? r_ptr : t_ptr;
+    const std::vector<int32_t>& col = is_user ? r_col : t_col;
+    const std::vector<float>& val = is_user ? r_val : t_val;
+    float rs = 0.f;
+    for (int32_t p = ptr[(size_t)lr]; p < ptr[(size_t)lr + 1]; ++p) {
+      colidx[o] = is_user ? col[(size_t)p] + n_users : col[(size_t)p];
+      vals[o] = val[(size_t)p];
+      rs += val[(size_t)p];
+      ++o;
+    }
+    rowptr[(size_t)r + 1] = (int32_t)o;
+    if (rowsum) rowsum[r] = rs;
+  }
+  *nnz_out = o;
+  return SRB_OK;
+}
