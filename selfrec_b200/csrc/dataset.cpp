@@ -60,7 +60,8 @@ bool read_file(const char* path, std::vector<char>& out) {
   return true;
 }
 
-inline bool py_space(char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\n' || c == '\v' || c == '\f'; }
+// what str.strip() removes among the ASCII characters (\x1c-\x1f count as whitespace for str)
+inline bool py_space(char c) { return c == ' ' || (c >= '\t' && c <= '\r') || (c >= 0x1c && c <= 0x1f); }
 
 struct Triple {
   std::string_view u, i;
