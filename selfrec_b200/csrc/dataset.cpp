@@ -104,8 +104,9 @@ bool for_each_line(const std::vector<char>& buf, const char* what, F&& fn) {
   const char* end = p + buf.size();
   long line_no = 0;
   while (p < end) {
-    const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
-    const char* le = nl ? nl : end;
+    // universal newlines, as Python's text mode reads them: \n, \r\n and a lone \r all end a line
+    const char* le = p;
+    while (le < end && *le != '\n' && *le != '\r') ++le;
     ++line_no;
     Triple t;
     if (parse_line(p, le, t)) {
@@ -113,7 +114,8 @@ bool for_each_line(const std::vector<char>& buf, const char* what, F&& fn) {
       return false;
     }
     fn(t);
-    p = nl ? nl + 1 : end;
+    if (le < end && *le == '\r' && le + 1 < end && le[1] == '\n') ++le;
+    p = le < end ? le + 1 : end;
   }
   return true;
 }

@@ -35,13 +35,12 @@ _line = st.tuples(_name, _name, st.sampled_from(["1", "1.0", "3", "0.5", "2e0", 
 
 @settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
 @given(train=st.lists(_line, min_size=1, max_size=120), test=st.lists(_line, min_size=0, max_size=40),
-       crlf=st.booleans(), final_newline=st.booleans())
-def test_native_dataset_builder_equals_python_route(lib, tmp_path_factory, train, test, crlf, final_newline):
+       eol=st.sampled_from(["\n", "\r\n", "\r"]), final_newline=st.booleans())
+def test_native_dataset_builder_equals_python_route(lib, tmp_path_factory, train, test, eol, final_newline):
     from selfrec_b200.data.loader import FileIO
     from selfrec_b200.data.native import load_interaction
     from selfrec_b200.data.ui_graph import Interaction
     d = tmp_path_factory.mktemp("ds")
-    eol = "\r\n" if crlf else "\n"
     tr, te = d / "train.txt", d / "test.txt"
     tr.write_bytes((eol.join(" ".join(x) for x in train) + (eol if final_newline else "")).encode())
     te.write_bytes((eol.join(" ".join(x) for x in test) + (eol if (final_newline and test) else "")).encode())
