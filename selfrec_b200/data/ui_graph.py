@@ -22,10 +22,7 @@ def _native_unit_laplacian(adj_mat):
     m = sp.csr_matrix(adj_mat)
     if m.nnz == 0 or m.dtype != np.float32 or not m.has_canonical_format or not np.all(m.data == 1.0):
         return None
-    try:
-        lib = _lib.load()
-    except Exception:  # the library is optional for this host-side helper
-        return None
+    lib = _lib.load()  # a missing library is an error here as everywhere else
     U, I = m.shape
     n, k = U + I, int(m.nnz)
     rows = np.repeat(np.arange(U, dtype=np.int32), np.diff(m.indptr))
