@@ -48,6 +48,23 @@ int srb_device_ok(void);
  *   layer sum  LightGCN.py:74-75 / XSimGCL.py:95-96 (torch.stack + torch.mean)
  *   Adam       torch.optim.Adam.step (XSimGCL.py:25,37) when the product is the E0 gradient.
  * ------------------------------------------------------------------------------------- */
+/* Split ("huge") rows.  A power-law graph at config-5 scale (10 M x 2 M x 200 M) has rows with millions of
+ * non-zeros; rows with at least SRB_HUB_MIN_NNZ non-zeros are cut into chunks of SRB_HUB_CHUNK non-zeros, one CTA
+ * per chunk writes its partial sum to `part`, and the row's owner adds the partials in chunk order (deterministic).
+ * Static lists (built with the graph): the first n_rows entries of row_order are the split rows, first[r] is the
+ * slot of row r's first chunk, work[w] = (row, chunk index), n_work chunks in total.  Device-classified lists
+ * (srb_build_batch_rows): first / work are written on the device, n_work is the capacity and the live counts come
+ * from n_vlong_dev[0] (rows) and n_vlong_dev[4] (chunks). */
+#define SRB_HUB_CHUNK 2048
+#define SRB_HUB_MIN_NNZ 4096
+typedef struct srb_hub_split {
+  int32_t n_rows;
+  int32_t n_work;
+  const int32_t* first; /* [n_rows] */
+  const int32_t* work;  /* [n_work][2] */
+  float* part;          /* [n_work, d] scratch (one product at a time per graph) */
+} srb_hub_split;
+
 typedef struct srb_spmm_desc {
   /* A: CSR [n_rows, n_cols] */
   const int32_t* rowptr;
@@ -57,14 +74,15 @@ typedef struct srb_spmm_desc {
   int32_t n_cols;
   int32_t d;
   /* optional processing order of rows (length n_rows), NULL = natural order; when it is sorted by
-   * descending degree, the first n_vlong_rows entries are given a whole CTA each and the next
-   * n_long_rows entries a whole warp each (the rest share warps) */
+   * descending degree, the first hub.n_rows entries are split rows (see srb_hub_split), the next n_vlong_rows
+   * entries are given a whole CTA each and the next n_long_rows entries a whole warp each (the rest share warps) */
   const int32_t* row_order;
   int32_t n_long_rows;
   int32_t n_vlong_rows;
+  srb_hub_split hub;
   /* optional device-side classification (row lists built on the device, e.g. the rows of a batch):
-   * n_vlong_dev[0..2] = number of very long / long / short rows; row_order then holds three segments
-   * of capacity n_rows each: [0, n_rows) very long, [n_rows, 2 n_rows) long, [2 n_rows, 3 n_rows) short */
+   * n_vlong_dev[0..3] = number of split / very long / long / short rows, [4] = number of chunks; row_order then
+   * holds four segments of capacity n_rows each: split, very long, long, short */
   const int32_t* n_vlong_dev;
   /* optional bitmap over columns (bit c of word c/32): a clear bit promises X[c,:] == 0, so the
      non-zero is skipped without touching X (row-sparse X: the first backward product). */
@@ -108,6 +126,7 @@ typedef struct srb_encoder_desc {
   const int32_t* row_order;
   int32_t n_long_rows;
   int32_t n_vlong_rows;
+  srb_hub_split hub;
   int32_t n;
   int32_t d;
   int32_t n_layers;
@@ -123,7 +142,8 @@ typedef struct srb_encoder_desc {
    * the batch rows of a training step -- nothing else reads the final mean there */
   const int32_t* last_rows;
   int32_t n_last_rows;
-  const int32_t* last_rows_nv_dev; /* device-classified list: class sizes [3]; last_rows = 3 segments of n_last_rows (see srb_spmm_desc.n_vlong_dev) */
+  const int32_t* last_rows_nv_dev; /* device-classified list: counts [5]; last_rows = 4 segments of n_last_rows (see srb_spmm_desc.n_vlong_dev) */
+  srb_hub_split last_rows_hub;     /* split rows of that list (device-written first / work) */
   float* last_rows_out; /* [n, d], required with last_rows: receives the final mean of the listed rows
                            (final_out then only holds the running sum; the list may contain duplicates,
                            so the last layer must not update the running sum in place) */
@@ -309,15 +329,18 @@ int srb_topk_rows(const float* scores, int32_t n_q, int32_t n_items, int32_t k, 
  * exactly as CPython would. */
 int srb_random_sample_range(uint32_t* mt625, int64_t n, int64_t k, int32_t use_pool, int64_t* out);
 
-/* Rows of the [N, d] tables a batch touches (u, U + i, U + j; batch = srb_sampler_next_batch layout), listed for
- * srb_spmm_desc.n_vlong_dev: rows[3][3*batch_cap] by degree class (a CTA per long row, a warp per other row),
- * counters[4] = class sizes, row_mask (optional, (n_total_rows+31)/32 words) = bitmap of all batch rows for
- * srb_spmm_desc.col_mask.  Row-sharded tables: only rows in [row_begin, row_begin + n_local_rows) are listed, as
- * local ids of the rank's CSR slice (rowptr).  This is what lets the last forward layer of a training step
- * (nothing but the batch rows of the final mean is read, XSimGCL.py:30,45-50) skip every other row. */
+/* Rows of the [N, d] tables a batch touches (u, U + i, U + j; batch = srb_sampler_next_batch layout), each listed
+ * ONCE, for srb_spmm_desc.n_vlong_dev: rows[4][3*batch_cap] by degree class (split rows, a CTA per long row, a warp per
+ * other row), counters[8]: [0..3] class sizes, [4] chunks of the split rows; row_mask ((n_total_rows+31)/32 words,
+ * required: it is also what de-duplicates the list) = bitmap of all batch rows for srb_spmm_desc.col_mask.
+ * hub_first[3*batch_cap] / hub_work[hub_work_cap][2] (optional) receive the split-row lists; without them long rows
+ * get a CTA each.  Row-sharded tables: only rows in [row_begin, row_begin + n_local_rows) are listed, as local ids
+ * of the rank's CSR slice (rowptr).  This is what lets the last forward layer of a training step (nothing but the
+ * batch rows of the final mean is read, XSimGCL.py:30,45-50) skip every other row. */
 int srb_build_batch_rows(const int32_t* batch, int32_t batch_cap, int32_t n_users, const int32_t* rowptr,
                          int32_t row_begin, int32_t n_local_rows, int32_t n_total_rows, int32_t* rows,
-                         int32_t* counters, uint32_t* row_mask, void* stream);
+                         int32_t* counters, uint32_t* row_mask, int32_t* hub_first, int32_t* hub_work,
+                         int32_t hub_work_cap, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Native dataset -> CSR builder (host C++).  Replaces the Python loops of
@@ -355,6 +378,51 @@ int srb_bipartite_adjacency_csr(const int32_t* users, const int32_t* items, int6
                                 int64_t* nnz_out);
 
 /* ---------------------------------------------------------------------------------------
+ * Device-side assembly of the normalised (U+I) x (U+I) adjacency:
+ *   Interaction.__create_sparse_bipartite_adjacency / convert_to_laplacian_mat  data/ui_graph.py:47-65
+ *   Graph.normalize_graph_mat                                                  data/graph.py:10-24
+ * for the interaction edges that survive GraphAugmentor.edge_dropout / node_dropout (data/augmentor.py:11-40,
+ * SGL.py:80-96) -- or all of them (a config-5 sized graph is built this way: no scipy at 200 M edges).
+ * Inputs (device): the users x items CSR of distinct pairs, columns ascending (ui_ptr[U+1], ui_col[nnz], ui_val[nnz]
+ * = multiplicities, NULL = 1), its transpose (iu_ptr[I+1], iu_col[nnz] user ids ascending, iu_perm[nnz] = position
+ * in the ui order of each entry of the iu order), the kept edges as byte flags over the ui order (keep_flags) or as
+ * a list of positions (keep_idx, n_keep; e.g. srb_random_sample_range's output) or neither (all edges);
+ * reset_weights != 0 gives kept edges weight 1 (augmentor.py:36 np.ones_like).
+ * dinv_table[k] = float32 power(k, -0.5) with inf -> 0 for k = 0 .. dinv_table_n-1, computed by the caller with
+ * numpy so that the rounding is the reference's (row sums are small integers).
+ * Outputs (device): rowptr[N+1], colidx / vals[out_cap >= 2 * kept] (columns ascending, values the fp32 products
+ * (d[r] * a) * d[c] of graph.py:16-18), dinv[N], *nnz_out (optional) = stored entries.  Results are bit-identical
+ * to the scipy route (tests/test_gpu_graphbuild.py).  Stream-ordered; workspace from
+ * srb_graph_assemble_workspace_bytes, 256-byte aligned.
+ * ------------------------------------------------------------------------------------- */
+typedef struct srb_graph_assemble_desc {
+  int32_t n_users, n_items;
+  int64_t nnz;
+  const int32_t* ui_ptr;
+  const int32_t* ui_col;
+  const float* ui_val;
+  const int32_t* iu_ptr;
+  const int32_t* iu_col;
+  const int32_t* iu_perm;
+  const uint8_t* keep_flags;
+  const int64_t* keep_idx;
+  int64_t n_keep;
+  int32_t reset_weights;
+  const float* dinv_table;
+  int32_t dinv_table_n;
+  int32_t* rowptr;
+  int32_t* colidx;
+  float* vals;
+  float* dinv;
+  int64_t out_cap;
+  int64_t* nnz_out;
+  void* workspace;
+  int64_t workspace_bytes;
+} srb_graph_assemble_desc;
+int64_t srb_graph_assemble_workspace_bytes(int32_t n_users, int32_t n_items, int64_t nnz);
+int srb_graph_assemble(const srb_graph_assemble_desc* desc, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Ranking metrics, device part (util/evaluation.py:9-15 `hits`, :85-97 NDCG):
  * hit_mask[q] bit r = 1 iff topk_ids[q, r] is in the test set of users[q]  (r < k <= 64).
  * test_ptr / test_idx: CSR over user ids of the test items that have a training id, sorted per
@@ -382,6 +450,7 @@ typedef struct srb_graph_csr {
   const int32_t* row_order;
   int32_t n_long_rows;
   int32_t n_vlong_rows;
+  srb_hub_split hub;
 } srb_graph_csr;
 
 typedef struct srb_step_desc {
@@ -410,7 +479,8 @@ typedef struct srb_step_desc {
   int64_t workspace_bytes; /* >= srb_step_workspace_bytes */
 } srb_step_desc;
 
-int64_t srb_step_workspace_bytes(int32_t model, int32_t n, int32_t d, int32_t batch_cap);
+/* n_hub_work: adj.hub.n_work of the clean graph (chunks of its split rows; 0 when it has none) */
+int64_t srb_step_workspace_bytes(int32_t model, int32_t n, int32_t d, int32_t batch_cap, int32_t n_hub_work);
 int srb_train_step(const srb_step_desc* desc, void* stream);
 
 /* batch buffer layout (int32 words): [0]=b [1]=n_uniq_u [2]=n_uniq_i [3]=reserved

@@ -21,11 +21,19 @@ class SrbError(RuntimeError):
     pass
 
 
+class HubSplit(C.Structure):
+    _fields_ = [("n_rows", C.c_int32), ("n_work", C.c_int32), ("first", VP), ("work", VP), ("part", VP)]
+
+
+HUB_CHUNK = 2048    # SRB_HUB_CHUNK
+HUB_MIN_NNZ = 4096  # SRB_HUB_MIN_NNZ
+
+
 class SpmmDesc(C.Structure):
     _fields_ = [
         ("rowptr", VP), ("colidx", VP), ("vals", VP),
         ("n_rows", C.c_int32), ("n_cols", C.c_int32), ("d", C.c_int32),
-        ("row_order", VP), ("n_long_rows", C.c_int32), ("n_vlong_rows", C.c_int32), ("n_vlong_dev", VP), ("col_mask", VP), ("X", VP), ("Y", VP), ("extra", VP), ("extra_scale", C.c_float),
+        ("row_order", VP), ("n_long_rows", C.c_int32), ("n_vlong_rows", C.c_int32), ("hub", HubSplit), ("n_vlong_dev", VP), ("col_mask", VP), ("X", VP), ("Y", VP), ("extra", VP), ("extra_scale", C.c_float),
         ("noise_mode", C.c_int32), ("noise", VP), ("eps", C.c_float),
         ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64), ("philox_step_dev", VP),
         ("sum_in", VP), ("sum_out", VP), ("sum_scale", C.c_float),
@@ -37,10 +45,10 @@ class SpmmDesc(C.Structure):
 class EncoderDesc(C.Structure):
     _fields_ = [
         ("rowptr", VP), ("colidx", VP), ("vals", VP), ("row_order", VP), ("n_long_rows", C.c_int32),
-        ("n_vlong_rows", C.c_int32), ("n", C.c_int32), ("d", C.c_int32), ("n_layers", C.c_int32), ("include_ego", C.c_int32),
+        ("n_vlong_rows", C.c_int32), ("hub", HubSplit), ("n", C.c_int32), ("d", C.c_int32), ("n_layers", C.c_int32), ("include_ego", C.c_int32),
         ("layer_cl", C.c_int32), ("noise_mode", C.c_int32), ("noise", VP), ("eps", C.c_float),
         ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64), ("philox_step_dev", VP),
-        ("last_rows", VP), ("n_last_rows", C.c_int32), ("last_rows_nv_dev", VP), ("last_rows_out", VP),
+        ("last_rows", VP), ("n_last_rows", C.c_int32), ("last_rows_nv_dev", VP), ("last_rows_hub", HubSplit), ("last_rows_out", VP),
         ("E0", VP), ("final_out", VP), ("cl_out", VP), ("work0", VP), ("work1", VP),
     ]
 
@@ -83,7 +91,17 @@ class TopkDesc(C.Structure):
 
 
 class GraphCsr(C.Structure):
-    _fields_ = [("rowptr", VP), ("colidx", VP), ("vals", VP), ("row_order", VP), ("n_long_rows", C.c_int32), ("n_vlong_rows", C.c_int32)]
+    _fields_ = [("rowptr", VP), ("colidx", VP), ("vals", VP), ("row_order", VP), ("n_long_rows", C.c_int32), ("n_vlong_rows", C.c_int32),
+                ("hub", HubSplit)]
+
+
+class GraphAssembleDesc(C.Structure):
+    _fields_ = [
+        ("n_users", C.c_int32), ("n_items", C.c_int32), ("nnz", C.c_int64), ("ui_ptr", VP), ("ui_col", VP), ("ui_val", VP),
+        ("iu_ptr", VP), ("iu_col", VP), ("iu_perm", VP), ("keep_flags", VP), ("keep_idx", VP), ("n_keep", C.c_int64),
+        ("reset_weights", C.c_int32), ("dinv_table", VP), ("dinv_table_n", C.c_int32), ("rowptr", VP), ("colidx", VP),
+        ("vals", VP), ("dinv", VP), ("out_cap", C.c_int64), ("nnz_out", VP), ("workspace", VP), ("workspace_bytes", C.c_int64),
+    ]
 
 
 class StepDesc(C.Structure):
@@ -124,7 +142,7 @@ SYMBOLS = {
     "srb_scatter_add_segments": (C.c_int, [VP, C.c_int32, C.c_int32, VP, VP]),
     "srb_rank_hit_masks": (C.c_int, [VP, C.c_int32, C.c_int32, VP, VP, VP, VP, VP]),
     "srb_random_sample_range": (C.c_int, [VP, C.c_int64, C.c_int64, C.c_int32, VP]),
-    "srb_build_batch_rows": (C.c_int, [VP, C.c_int32, C.c_int32, VP, C.c_int32, C.c_int32, C.c_int32, VP, VP, VP, VP]),
+    "srb_build_batch_rows": (C.c_int, [VP, C.c_int32, C.c_int32, VP, C.c_int32, C.c_int32, C.c_int32, VP, VP, VP, VP, VP, C.c_int32, VP]),
     "srb_dataset_load": (VP, [C.c_char_p, C.c_char_p]),
     "srb_dataset_free": (None, [VP]),
     "srb_dataset_counts": (C.c_int, [VP, VP]),
@@ -133,6 +151,8 @@ SYMBOLS = {
     "srb_dataset_interaction_csr": (C.c_int, [VP, VP, VP, VP]),
     "srb_dataset_adjacency_csr": (C.c_int, [VP, VP, VP, VP, VP, VP]),
     "srb_bipartite_adjacency_csr": (C.c_int, [VP, VP, C.c_int64, C.c_int32, C.c_int32, VP, VP, VP, VP, VP]),
+    "srb_graph_assemble_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int64]),
+    "srb_graph_assemble": (C.c_int, [C.POINTER(GraphAssembleDesc), VP]),
     "srb_adam_prepare": (C.c_int, [VP, VP, C.c_double, C.c_double, C.c_double, VP]),
     "srb_adam_step": (C.c_int, [VP, VP, VP, VP, C.c_int64, VP, C.c_double, C.c_double, C.c_float, VP]),
     "srb_topk_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
@@ -140,7 +160,7 @@ SYMBOLS = {
     "srb_score_topk": (C.c_int, [C.POINTER(TopkDesc), VP]),
     "srb_score_rows": (C.c_int, [VP, VP, C.c_int32, VP, C.c_int32, C.c_int32, VP, VP]),
     "srb_topk_rows": (C.c_int, [VP, C.c_int32, C.c_int32, C.c_int32, VP, VP, VP]),
-    "srb_step_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "srb_step_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "srb_train_step": (C.c_int, [C.POINTER(StepDesc), VP]),
     "srb_sampler_create": (VP, [c_i32p, c_i32p, C.c_int64, C.c_int32, C.c_int32]),
     "srb_sampler_destroy": (None, [VP]),

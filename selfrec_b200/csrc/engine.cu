@@ -34,9 +34,13 @@ struct Ws {
   float* nce_losses;   // [4]
   int32_t* idx_cat;    // [2B] SGL concatenated unique ids
   int32_t* n_cat;      // [1]
-  int32_t* batch_rows; // [3][3B] table rows of the batch (u, U+i, U+j) by degree class: >= 256, >= 64, shorter
-  int32_t* n_hub;      // [3] rows per class
+  int32_t* batch_rows; // [4][3B] distinct table rows of the batch (u, U+i, U+j) by class: split, CTA, warp, lane group
+  int32_t* n_hub;      // [8] rows per class [0..3], chunks of the split rows [4]
   uint32_t* row_mask;  // [(N+31)/32] bitmap of the batch's table rows (the rows the gradient seed touches)
+  int32_t* hub_first;  // [3B] first chunk slot of each split batch row
+  int32_t* hub_work;   // [hub_cap][2]
+  float* hub_part;     // [hub_cap, d]
+  int32_t hub_cap;
   void* nce_ws;
   int64_t nce_ws_bytes;
 };
@@ -72,10 +76,14 @@ static int64_t carve(const srb_step_desc* s, Ws* w, char* base) {
   float* f_nl = (float*)take(4 * 4);
   int32_t* i_cat = (int32_t*)take(2 * B * 4);
   int32_t* i_ncat = (int32_t*)take(4);
-  int32_t* i_brows = (int32_t*)take(3 * 3 * B * 4);
-  // [n_hub, back counter, pad, pad | row bitmap]: one memset clears all of it
-  int32_t* i_nhub = (int32_t*)take(graph ? 16 + ((N + 31) / 32) * 4 : 16);
-  uint32_t* u_mask = (uint32_t*)(i_nhub + 4);
+  int32_t* i_brows = (int32_t*)take(4 * 3 * B * 4);
+  // [class counters (8 words) | row bitmap]: one memset clears all of it
+  int32_t* i_nhub = (int32_t*)take(graph ? 32 + ((N + 31) / 32) * 4 : 32);
+  uint32_t* u_mask = (uint32_t*)(i_nhub + 8);
+  const int64_t hub_cap = graph ? s->adj.hub.n_work : 0;  // distinct batch rows: never more chunks than the whole graph has
+  int32_t* i_hfirst = (int32_t*)take(hub_cap ? 3 * B * 4 : 0);
+  int32_t* i_hwork = (int32_t*)take(hub_cap * 2 * 4);
+  float* f_hpart = (float*)take(hub_cap * d * 4);
   const int64_t nws = has_cl ? srb_infonce_workspace_bytes((int32_t)(2 * B), (int32_t)d, 2) : 0;
   void* v_nws = take(nws);
   if (w) {
@@ -99,6 +107,10 @@ static int64_t carve(const srb_step_desc* s, Ws* w, char* base) {
     w->batch_rows = i_brows;
     w->n_hub = i_nhub;
     w->row_mask = u_mask;
+    w->hub_first = i_hfirst;
+    w->hub_work = i_hwork;
+    w->hub_part = f_hpart;
+    w->hub_cap = (int32_t)hub_cap;
     w->nce_ws = v_nws;
     w->nce_ws_bytes = nws;
   }
@@ -115,27 +127,30 @@ __global__ void build_cat_idx_kernel(const int32_t* batch, int cap, int n_users,
   if (blockIdx.x == 0 && threadIdx.x == 0) *n_cat = nu + ni;
 }
 
-// rows of the [N, d] tables a batch touches: u, U + i, U + j, classified by degree on the fly for the
-// last-layer SpMM (a CTA per long row, a warp per other row; the lane-group class stays empty) into
-// three segments of capacity 3*cap; counters[c] ends up as the size of class c.  Also sets the rows'
-// bits in row_mask.  counters[0..3] and row_mask are zeroed by the caller.
+// rows of the [N, d] tables a batch touches: u, U + i, U + j, each listed ONCE (the bitmap de-duplicates: a hub user
+// sits in a batch many times) and classified by degree on the fly for the last-layer SpMM -- split rows (their
+// chunks go to hub_work), a CTA per long row, a warp per other row; the lane-group class stays empty -- into four
+// segments of capacity 3*cap; counters[c] ends up as the size of class c, counters[4] as the number of chunks.
+// counters[0..7] and row_mask are zeroed by the caller.
 // With a row range [row_begin, row_begin + n_local) (row-sharded tables) only the rows of that range are listed,
 // as LOCAL row ids of the rank's CSR slice; the bitmap always covers all batch rows (global ids).
 __global__ void __launch_bounds__(256) build_batch_rows_kernel(const int32_t* batch, int cap, int n_users, const int32_t* rowptr,
                                                                int row_begin, int n_local, int32_t* rows, int32_t* counters,
-                                                               uint32_t* row_mask) {
+                                                               uint32_t* row_mask, int32_t* hub_first, int32_t* hub_work,
+                                                               int hub_cap) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = min(batch[0], cap);
   const int sec = t / cap, k = t % cap;
   if (sec >= 3 || k >= b) return;
   const int32_t* u = batch + SRB_BATCH_HEADER;
   const int grow = (sec == 0) ? u[k] : n_users + u[sec * cap + k];
-  if (row_mask) atomicOr(row_mask + (grow >> 5), 1u << (grow & 31));
+  const uint32_t bit = 1u << (grow & 31);
+  if (atomicOr(row_mask + (grow >> 5), bit) & bit) return;  // listed already
   const int row = grow - row_begin;
   if (row < 0 || row >= n_local) return;
   const int deg = rowptr[row + 1] - rowptr[row];
   // only ~3B rows: parallelism is scarce, so no row shares a warp and rows above 4 warp-iterations get a CTA
-  const int cls = deg >= 128 ? 0 : 1;
+  const int cls = (hub_first && deg >= SRB_HUB_MIN_NNZ) ? 0 : (deg >= 128 ? 1 : 2);
   // warp-aggregated slot allocation per class
   const unsigned mine = __match_any_sync(__activemask(), cls);
   const int lane = threadIdx.x & 31;
@@ -143,7 +158,17 @@ __global__ void __launch_bounds__(256) build_batch_rows_kernel(const int32_t* ba
   int base = 0;
   if (lane == leader) base = atomicAdd(counters + cls, __popc(mine));
   base = __shfl_sync(mine, base, leader);
-  rows[cls * 3 * cap + base + __popc(mine & ((1u << lane) - 1))] = row;
+  const int slot = base + __popc(mine & ((1u << lane) - 1));
+  rows[cls * 3 * cap + slot] = row;
+  if (cls == 0) {
+    const int nch = (deg + SRB_HUB_CHUNK - 1) / SRB_HUB_CHUNK;
+    const int first = atomicAdd(counters + 4, nch);
+    hub_first[slot] = first;
+    for (int c = 0; c < nch && first + c < hub_cap; ++c) {
+      hub_work[2 * (first + c)] = row;
+      hub_work[2 * (first + c) + 1] = c;
+    }
+  }
 }
 
 __global__ void finalize_losses_kernel(const float* bpr_losses, const float* nce_losses, int n_nce, float cl_rate, float* out) {
@@ -175,6 +200,7 @@ static int spmm_simple(const srb_step_desc* s, const srb_graph_csr* g, const flo
   p.row_order = g->row_order;
   p.n_long_rows = g->n_long_rows;
   p.n_vlong_rows = g->n_vlong_rows;
+  p.hub = g->hub;
   p.n_rows = p.n_cols = s->n_users + s->n_items;
   p.d = s->d;
   p.X = x;
@@ -269,6 +295,7 @@ static int encoder(const srb_step_desc* s, const Ws& w, const srb_graph_csr* g, 
   e.row_order = g->row_order;
   e.n_long_rows = g->n_long_rows;
   e.n_vlong_rows = g->n_vlong_rows;
+  e.hub = g->hub;
   e.n = s->n_users + s->n_items;
   e.d = s->d;
   e.n_layers = s->n_layers;
@@ -287,6 +314,7 @@ static int encoder(const srb_step_desc* s, const Ws& w, const srb_graph_csr* g, 
     e.last_rows = w.batch_rows;
     e.n_last_rows = 3 * s->batch_cap;
     e.last_rows_nv_dev = w.n_hub;
+    e.last_rows_hub = srb_hub_split{0, w.hub_cap, w.hub_first, w.hub_work, w.hub_part};
     e.last_rows_out = final_out;  // batch rows of the mean land here; the running sum lives in w.rsum
     e.final_out = w.rsum;
   }
@@ -298,8 +326,9 @@ static int encoder(const srb_step_desc* s, const Ws& w, const srb_graph_csr* g, 
 
 }  // namespace srb
 
-extern "C" int64_t srb_step_workspace_bytes(int32_t model, int32_t n, int32_t d, int32_t batch_cap) {
+extern "C" int64_t srb_step_workspace_bytes(int32_t model, int32_t n, int32_t d, int32_t batch_cap, int32_t n_hub_work) {
   srb_step_desc s = {};
+  s.adj.hub.n_work = n_hub_work > 0 ? n_hub_work : 0;
   s.model = model;
   s.n_users = n;
   s.n_items = 0;
@@ -318,7 +347,7 @@ extern "C" int srb_train_step(const srb_step_desc* s, void* stream) {
   SRB_REQUIRE(s->model == SRB_MODEL_MF || s->n_layers >= 1, "step: graph models need n_layers >= 1");
   SRB_REQUIRE(s->model == SRB_MODEL_MF || (s->adj.rowptr && s->adj.colidx && s->adj.vals), "step: null adjacency");
   const int N = s->n_users + s->n_items;
-  const int64_t need = srb_step_workspace_bytes(s->model, N, s->d, s->batch_cap);
+  const int64_t need = srb_step_workspace_bytes(s->model, N, s->d, s->batch_cap, s->model != SRB_MODEL_MF ? s->adj.hub.n_work : 0);
   SRB_REQUIRE(s->workspace && s->workspace_bytes >= need, "step: workspace too small (%lld < %lld)",
               (long long)s->workspace_bytes, (long long)need);
   SRB_REQUIRE(((uintptr_t)s->workspace & 255) == 0, "step: workspace must be 256-byte aligned");
@@ -340,9 +369,9 @@ extern "C" int srb_train_step(const srb_step_desc* s, void* stream) {
 
   // ---- forward ----
   if (s->model != SRB_MODEL_MF) {
-    SRB_TRY(check_cuda(cudaMemsetAsync(w.n_hub, 0, 16 + (size_t)((U + s->n_items + 31) / 32) * 4, st), "row mask memset"));
+    SRB_TRY(check_cuda(cudaMemsetAsync(w.n_hub, 0, 32 + (size_t)((U + s->n_items + 31) / 32) * 4, st), "row mask memset"));
     build_batch_rows_kernel<<<(3 * B + 255) / 256, 256, 0, st>>>(s->batch, B, U, s->adj.rowptr, 0, U + s->n_items, w.batch_rows, w.n_hub,
-                                                                   w.row_mask);
+                                                                   w.row_mask, w.hub_cap ? w.hub_first : nullptr, w.hub_work, w.hub_cap);
     SRB_TRY(post_launch("build_batch_rows_kernel"));
   }
   const float* table = s->params;  // table BPR gathers from
@@ -508,14 +537,15 @@ extern "C" int srb_train_step(const srb_step_desc* s, void* stream) {
 
 extern "C" int srb_build_batch_rows(const int32_t* batch, int32_t batch_cap, int32_t n_users, const int32_t* rowptr, int32_t row_begin,
                                     int32_t n_local_rows, int32_t n_total_rows, int32_t* rows, int32_t* counters, uint32_t* row_mask,
-                                    void* stream) {
-  SRB_REQUIRE(batch && rowptr && rows && counters, "build_batch_rows: null pointer");
+                                    int32_t* hub_first, int32_t* hub_work, int32_t hub_work_cap, void* stream) {
+  SRB_REQUIRE(batch && rowptr && rows && counters && row_mask, "build_batch_rows: null pointer");
   SRB_REQUIRE(batch_cap > 0 && row_begin >= 0 && n_local_rows >= 0 && row_begin + n_local_rows <= n_total_rows,
               "build_batch_rows: bad shape");
+  SRB_REQUIRE(!hub_first || (hub_work && hub_work_cap > 0), "build_batch_rows: split-row lists incomplete");
   cudaStream_t st = (cudaStream_t)stream;
-  SRB_TRY(srb::check_cuda(cudaMemsetAsync(counters, 0, 16, st), "batch rows memset"));
-  if (row_mask) SRB_TRY(srb::check_cuda(cudaMemsetAsync(row_mask, 0, (size_t)((n_total_rows + 31) / 32) * 4, st), "row mask memset"));
+  SRB_TRY(srb::check_cuda(cudaMemsetAsync(counters, 0, 32, st), "batch rows memset"));
+  SRB_TRY(srb::check_cuda(cudaMemsetAsync(row_mask, 0, (size_t)((n_total_rows + 31) / 32) * 4, st), "row mask memset"));
   srb::build_batch_rows_kernel<<<(3 * batch_cap + 255) / 256, 256, 0, st>>>(batch, batch_cap, n_users, rowptr, row_begin, n_local_rows,
-                                                                           rows, counters, row_mask);
+                                                                           rows, counters, row_mask, hub_first, hub_work, hub_work_cap);
   return srb::post_launch("build_batch_rows_kernel");
 }

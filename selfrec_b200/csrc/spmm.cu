@@ -18,8 +18,13 @@ struct SpmmArgs {
   int32_t n_rows;
   const int32_t* n_vlong_dev;  // optional device-side class split (see srb_spmm_desc)
   const uint32_t* col_mask;    // optional: clear bit = X row is zero
-  int32_t n_vlong; // leading entries of row_order that get a whole CTA
+  int32_t n_huge;  // leading entries of row_order that are split into SRB_HUB_CHUNK-sized chunks (spmm_hub_kernel)
+  int32_t n_vlong; // following entries that get a whole CTA
   int32_t n_long;  // following entries that get a whole warp
+  const int32_t* hub_first;  // [n_huge] first chunk slot of each split row
+  const int32_t* hub_work;   // [n_work][2] (row, chunk index)
+  int32_t n_work;
+  float* hub_part;           // [n_work, D] partial sums of the chunks
   const float* X;
   float* Y;
   const float* extra;
@@ -70,8 +75,10 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmArgs& a, int row, int gl
       } else {
         const uint32_t stp = a.pstep ? (uint32_t)*a.pstep : 0u;
         const uint32_t grow = (uint32_t)(a.row_begin + row);
-        const uint4 r0 = philox4x32_10(make_uint4(grow, (uint32_t)gl, a.poff.x, a.poff.y ^ stp), a.pkey);
-        const uint4 r1 = philox4x32_10(make_uint4(grow, (uint32_t)(gl + LPR), a.poff.x, a.poff.y ^ stp), a.pkey);
+        // counter = (row, column block | view << 16, layer tag, step): (view, step) pairs never share a stream
+        const uint32_t vw = a.poff.y << 16;
+        const uint4 r0 = philox4x32_10(make_uint4(grow, (uint32_t)gl | vw, a.poff.x, stp), a.pkey);
+        const uint4 r1 = philox4x32_10(make_uint4(grow, (uint32_t)(gl + LPR) | vw, a.poff.x, stp), a.pkey);
         n0 = make_float4(u32_to_unit(r0.x), u32_to_unit(r0.y), u32_to_unit(r0.z), u32_to_unit(r0.w));
         n1 = make_float4(u32_to_unit(r1.x), u32_to_unit(r1.y), u32_to_unit(r1.z), u32_to_unit(r1.w));
       }
@@ -249,6 +256,80 @@ __device__ __forceinline__ void xor_reduce_groups(float4& acc0, float4& acc1, in
   }
 }
 
+// Partial sums of the chunks of split ("huge") rows: one CTA per (row, chunk) work item, SRB_HUB_CHUNK non-zeros each.
+// A power-law graph at config-5 scale has rows with millions of non-zeros; one CTA walking such a row alone would
+// take longer than the rest of the product, so those rows are cut into chunks here and summed (in chunk order:
+// deterministic) by the main kernel.
+template <int D, bool MASKED>
+__global__ void __launch_bounds__(256) spmm_hub_kernel(const SpmmArgs a) {
+  constexpr int LPR = D / 8;
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int grp = lane / LPR;
+  const int gl = lane % LPR;
+  const int n_work = a.n_vlong_dev ? min(a.n_vlong_dev[4], a.n_work) : a.n_work;
+  __shared__ float4 part[8][2][LPR];
+  for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+    const int row = __ldg(a.hub_work + 2 * w);
+    const int ci = __ldg(a.hub_work + 2 * w + 1);
+    const int rbeg = __ldg(a.rowptr + row), rend = __ldg(a.rowptr + row + 1);
+    const int beg = min(rend, rbeg + ci * SRB_HUB_CHUNK);
+    const int end = min(rend, beg + SRB_HUB_CHUNK);
+    constexpr int per = SRB_HUB_CHUNK / 8;  // non-zeros per warp, a multiple of 32
+    const int wbeg = beg + wib * per;
+    const int wend = min(end, wbeg + per);
+    float4 acc0 = f4_zero(), acc1 = f4_zero();
+    spmm_gather<D, MASKED>(a, wbeg + grp * LPR, wend, 32, gl, acc0, acc1);
+    xor_reduce_groups(acc0, acc1, LPR);
+    if (grp == 0) {
+      part[wib][0][gl] = acc0;
+      part[wib][1][gl] = acc1;
+    }
+    __syncthreads();
+    if (wib == 0 && grp == 0) {
+      acc0 = f4_zero();
+      acc1 = f4_zero();
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        acc0 = f4_add(acc0, part[q][0][gl]);
+        acc1 = f4_add(acc1, part[q][1][gl]);
+      }
+      float* dst = a.hub_part + (size_t)w * D + gl * 4;
+      st4(dst, acc0);
+      st4(dst + D / 2, acc1);
+    }
+    __syncthreads();
+  }
+}
+
+// Split rows, second half: add up the chunk sums of spmm_hub_kernel (chunk order), then the common epilogue.
+// One warp per row; its own launch so that the main kernel's register budget stays what it was.
+template <int D>
+__global__ void __launch_bounds__(256) spmm_hub_finish_kernel(const SpmmArgs a) {
+  constexpr int LPR = D / 8;
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int grp = lane / LPR;
+  const int gl = lane % LPR;
+  const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int n_huge = a.n_vlong_dev ? min(a.n_vlong_dev[0], a.n_rows) : a.n_huge;
+  for (int vr = warp0; vr < n_huge; vr += nwarps) {
+    const int row = __ldg(a.row_order + vr);
+    const int first = __ldg(a.hub_first + vr);
+    const int deg = __ldg(a.rowptr + row + 1) - __ldg(a.rowptr + row);
+    const int nch = (deg + SRB_HUB_CHUNK - 1) / SRB_HUB_CHUNK;
+    float4 acc0 = f4_zero(), acc1 = f4_zero();
+    for (int c = grp; c < nch; c += RPW) {
+      const float* src = a.hub_part + (size_t)(first + c) * D + gl * 4;
+      acc0 = f4_add(acc0, *reinterpret_cast<const float4*>(src));
+      acc1 = f4_add(acc1, *reinterpret_cast<const float4*>(src + D / 2));
+    }
+    xor_reduce_groups(acc0, acc1, LPR);
+    spmm_epilogue<D>(a, row, gl, acc0, acc1, grp == 0);
+  }
+}
+
 template <int D, bool MASKED>
 __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmArgs a) {
   constexpr int LPR = D / 8;     // lanes per row
@@ -260,17 +341,19 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmArgs a) {
   const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
 
-  int n_vlong = a.n_vlong, n_long = a.n_long, n_short = a.n_rows - a.n_vlong - a.n_long;
-  const int32_t* ro_v = a.row_order;  // the three classes' row lists (null: identity order)
-  const int32_t* ro_l = a.row_order ? a.row_order + n_vlong : nullptr;
+  // (the split rows -- the first n_huge entries of the list -- belong to spmm_hub_kernel / spmm_hub_finish_kernel)
+  int n_vlong = a.n_vlong, n_long = a.n_long, n_short = a.n_rows - a.n_huge - a.n_vlong - a.n_long;
+  const int32_t* ro_v = a.row_order ? a.row_order + a.n_huge : nullptr;  // the three classes' row lists (null: identity order)
+  const int32_t* ro_l = a.row_order ? ro_v + n_vlong : nullptr;
   const int32_t* ro_s = a.row_order ? ro_l + n_long : nullptr;
   int id_l = n_vlong, id_s = n_vlong + n_long;
-  if (a.n_vlong_dev) {  // row list classified on the device: three segments of capacity n_rows
-    n_vlong = min(a.n_vlong_dev[0], a.n_rows);
-    n_long = min(a.n_vlong_dev[1], a.n_rows);
-    n_short = min(a.n_vlong_dev[2], a.n_rows);
-    ro_l = a.row_order + a.n_rows;
-    ro_s = a.row_order + 2 * a.n_rows;
+  if (a.n_vlong_dev) {  // row list classified on the device: four segments of capacity n_rows (split, very long, long, short)
+    n_vlong = min(a.n_vlong_dev[1], a.n_rows);
+    n_long = min(a.n_vlong_dev[2], a.n_rows);
+    n_short = min(a.n_vlong_dev[3], a.n_rows);
+    ro_v = a.row_order + a.n_rows;
+    ro_l = a.row_order + 2 * a.n_rows;
+    ro_s = a.row_order + 3 * a.n_rows;
   }
   // ---- class 1: one CTA per very long row ----
   __shared__ float4 part[8][2][LPR];
@@ -326,21 +409,37 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmArgs a) {
   }
 }
 
+template <int D>
+static void launch_spmm_d(const SpmmArgs& a, int hub_blocks, int blocks, cudaStream_t st) {
+  const bool m = a.col_mask != nullptr;
+  if (hub_blocks > 0) {
+    if (m) spmm_hub_kernel<D, true><<<hub_blocks, 256, 0, st>>>(a);
+    else spmm_hub_kernel<D, false><<<hub_blocks, 256, 0, st>>>(a);
+    const int nh = a.n_vlong_dev ? a.n_rows : a.n_huge;  // (device-counted lists: the capacity)
+    spmm_hub_finish_kernel<D><<<max(1, min((nh + 7) / 8, hub_blocks)), 256, 0, st>>>(a);
+    g_launches.fetch_add(2, std::memory_order_relaxed);
+  }
+  if (m) spmm_csr_kernel<D, true><<<blocks, 256, 0, st>>>(a);
+  else spmm_csr_kernel<D, false><<<blocks, 256, 0, st>>>(a);
+}
+
 static int launch_spmm(const SpmmArgs& a, int d, cudaStream_t st) {
   if (a.n_rows == 0) return SRB_OK;
   const int threads = 256;
   const int rpw = 32 / (d / 8);
-  const long long items = (long long)a.n_long + ((long long)a.n_rows - a.n_vlong - a.n_long + rpw - 1) / rpw;
+  const long long items = (long long)a.n_long + ((long long)a.n_rows - a.n_huge - a.n_vlong - a.n_long + rpw - 1) / rpw;
   long long blocks = (items + threads / 32 - 1) / (threads / 32);
   if (a.n_vlong_dev) blocks = ((long long)a.n_rows + threads / 32 - 1) / (threads / 32);  // worst case: every row long, a warp each
   if (blocks < a.n_vlong) blocks = a.n_vlong;
   const long long cap = (long long)sm_count() * 8;  // 8 x 256 threads = full residency
   if (blocks > cap) blocks = cap;
-  const bool m = a.col_mask != nullptr;
+  if (blocks < 1) blocks = 1;
+  long long hub_blocks = a.n_work;  // (device-counted lists: the capacity)
+  if (hub_blocks > cap) hub_blocks = cap;
   switch (d) {
-    case 32: m ? spmm_csr_kernel<32, true><<<(int)blocks, threads, 0, st>>>(a) : spmm_csr_kernel<32, false><<<(int)blocks, threads, 0, st>>>(a); break;
-    case 64: m ? spmm_csr_kernel<64, true><<<(int)blocks, threads, 0, st>>>(a) : spmm_csr_kernel<64, false><<<(int)blocks, threads, 0, st>>>(a); break;
-    case 128: m ? spmm_csr_kernel<128, true><<<(int)blocks, threads, 0, st>>>(a) : spmm_csr_kernel<128, false><<<(int)blocks, threads, 0, st>>>(a); break;
+    case 32: launch_spmm_d<32>(a, (int)hub_blocks, (int)blocks, st); break;
+    case 64: launch_spmm_d<64>(a, (int)hub_blocks, (int)blocks, st); break;
+    case 128: launch_spmm_d<128>(a, (int)hub_blocks, (int)blocks, st); break;
     default: set_error("spmm: unsupported d=%d (32, 64, 128)", d); return SRB_ERR_ARG;
   }
   return post_launch("spmm_csr_kernel");
@@ -359,10 +458,20 @@ static int fill_args(const srb_spmm_desc* d, SpmmArgs& a) {
   a.vals = d->vals;
   a.row_order = d->row_order;
   a.n_rows = d->n_rows;
-  a.n_vlong = (d->row_order && d->n_vlong_rows > 0) ? (d->n_vlong_rows < d->n_rows ? d->n_vlong_rows : d->n_rows) : 0;
   a.n_vlong_dev = d->row_order ? d->n_vlong_dev : nullptr;
+  // split rows: static lists take the counts from the desc, device-classified lists from n_vlong_dev[0] / [4]
+  const bool hub = d->row_order && d->hub.n_work > 0 && (a.n_vlong_dev || d->hub.n_rows > 0);
+  SRB_REQUIRE(!hub || (d->hub.first && d->hub.work && d->hub.part), "spmm: split-row lists incomplete");
+  SRB_REQUIRE(!hub || d->hub.n_rows <= d->n_rows, "spmm: more split rows than rows");
+  a.n_huge = (hub && !a.n_vlong_dev) ? d->hub.n_rows : 0;
+  a.hub_first = hub ? d->hub.first : nullptr;
+  a.hub_work = hub ? d->hub.work : nullptr;
+  a.hub_part = hub ? d->hub.part : nullptr;
+  a.n_work = hub ? d->hub.n_work : 0;
+  const int rest = d->n_rows - a.n_huge;
+  a.n_vlong = (d->row_order && d->n_vlong_rows > 0) ? (d->n_vlong_rows < rest ? d->n_vlong_rows : rest) : 0;
   a.col_mask = d->col_mask;
-  a.n_long = (d->row_order && d->n_long_rows > 0) ? (d->n_long_rows < d->n_rows - a.n_vlong ? d->n_long_rows : d->n_rows - a.n_vlong) : 0;
+  a.n_long = (d->row_order && d->n_long_rows > 0) ? (d->n_long_rows < rest - a.n_vlong ? d->n_long_rows : rest - a.n_vlong) : 0;
   a.X = d->X;
   a.Y = d->Y;
   a.extra = d->extra;
@@ -455,6 +564,7 @@ extern "C" int srb_encoder_forward(const srb_encoder_desc* e, void* stream) {
     s.row_order = e->row_order;
     s.n_long_rows = e->n_long_rows;
     s.n_vlong_rows = e->n_vlong_rows;
+    s.hub = e->hub;
     s.n_rows = e->n;
     s.n_cols = e->n;
     s.d = e->d;
@@ -478,13 +588,15 @@ extern "C" int srb_encoder_forward(const srb_encoder_desc* e, void* stream) {
       // only the listed rows of the final mean are consumed: one warp per listed row
       s.row_order = e->last_rows;
       s.n_rows = e->n_last_rows;
-      if (e->last_rows_nv_dev) {  // list classified on the device: three segments of n_last_rows entries
+      if (e->last_rows_nv_dev) {  // list classified on the device: four segments of n_last_rows entries
         s.n_vlong_rows = 0;
         s.n_long_rows = 0;
         s.n_vlong_dev = e->last_rows_nv_dev;
+        s.hub = e->last_rows_hub;
       } else {
         s.n_vlong_rows = e->n_last_rows;  // unsorted, degree-biased rows: a CTA per listed row
         s.n_long_rows = 0;
+        s.hub = srb_hub_split{};
       }
       s.Y = nullptr;
       s.sum_out = e->last_rows_out;  // out of place: duplicates in the list stay idempotent

@@ -33,6 +33,13 @@ class TrainEngine:
                  layer_cl=0, l2_div=1.0, device=None, init_user=None, init_item=None, philox_seed=0x5EED):
         lib = _lib.require_device()
         self.lib = lib
+        if model not in _lib.MODEL_IDS:
+            raise ValueError(f"TrainEngine: unknown model {model!r} (one of {sorted(_lib.MODEL_IDS)})")
+        if int(emb_size) not in ops._SUPPORTED_D:
+            raise _lib.SrbError(f"TrainEngine: embedding.size {emb_size} is not supported by the CUDA path "
+                                f"(supported: {ops._SUPPORTED_D}); there is no fallback")
+        if int(batch_size) <= 0:
+            raise ValueError("TrainEngine: batch.size must be positive")
         self.model_name = model
         self.model_id = _lib.MODEL_IDS[model]
         self.data = data
@@ -42,12 +49,19 @@ class TrainEngine:
         self.B = int(batch_size)
         self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         dev = self.dev
-        if init_user is None:  # same initialiser calls, same order as LightGCN.py:60-66
-            init_user = torch.nn.init.xavier_uniform_(torch.empty(self.U, self.d))
-            init_item = torch.nn.init.xavier_uniform_(torch.empty(self.I, self.d))
         self.params = torch.empty((self.N, self.d), device=dev, dtype=torch.float32)
-        self.params[: self.U].copy_(init_user)
-        self.params[self.U:].copy_(init_item)
+        if init_user is None and self.N * self.d > (1 << 27):
+            # config-5 sized tables: xavier-uniform drawn on the device (a 6 GB host tensor is not worth its copy)
+            g = torch.Generator(device=dev).manual_seed(torch.initial_seed() & 0x7FFFFFFF)
+            for lo, hi in ((0, self.U), (self.U, self.N)):
+                bound = (6.0 / ((hi - lo) + self.d)) ** 0.5
+                self.params[lo:hi].uniform_(-bound, bound, generator=g)
+        else:
+            if init_user is None:  # same initialiser calls, same order as LightGCN.py:60-66
+                init_user = torch.nn.init.xavier_uniform_(torch.empty(self.U, self.d))
+                init_item = torch.nn.init.xavier_uniform_(torch.empty(self.I, self.d))
+            self.params[: self.U].copy_(init_user)
+            self.params[self.U:].copy_(init_item)
         self.m = torch.zeros_like(self.params)
         self.v = torch.zeros_like(self.params)
         self.step_dev = torch.zeros(1, device=dev, dtype=torch.int32)
@@ -60,12 +74,14 @@ class TrainEngine:
         self.ring_pos = 0
         self.loss_ring = [torch.zeros(4, dtype=torch.float32).pin_memory() for _ in range(8)]
         self.loss_pos = 0
-        ws_bytes = lib.srb_step_workspace_bytes(self.model_id, self.N, self.d, self.B)
-        self.workspace = torch.empty(ws_bytes + 256, device=dev, dtype=torch.uint8)
-        ws_ptr = (self.workspace.data_ptr() + 255) // 256 * 256
         self.adj = None
         if model != "MF":
-            self.adj = ops.SparseAdj(data.norm_adj).cuda(dev)
+            na = data.norm_adj
+            self.adj = na if isinstance(na, ops.SparseAdj) else ops.SparseAdj(na)
+            self.adj.cuda(dev)
+        ws_bytes = lib.srb_step_workspace_bytes(self.model_id, self.N, self.d, self.B, self.adj.n_work if self.adj is not None else 0)
+        self.workspace = torch.empty(ws_bytes + 256, device=dev, dtype=torch.uint8)
+        ws_ptr = (self.workspace.data_ptr() + 255) // 256 * 256
         self.view_adj = [None, None]
         self.noise = None
         s = _lib.StepDesc()
@@ -77,7 +93,7 @@ class TrainEngine:
         s.noise_mode = 2 if model in ("SimGCL", "XSimGCL") else 0
         s.philox_seed = int(philox_seed)
         if self.adj is not None:
-            s.adj = self.adj.graph_struct()
+            s.adj = self.adj.graph_struct(self.d)
         s.batch, s.params, s.adam_m, s.adam_v = ops._p(self.batch_dev), ops._p(self.params), ops._p(self.m), ops._p(self.v)
         s.step_dev, s.scalars, s.losses = ops._p(self.step_dev), ops._p(self.scalars), ops._p(self.losses)
         s.workspace, s.workspace_bytes = C.c_void_p(ws_ptr), ws_bytes
@@ -85,6 +101,7 @@ class TrainEngine:
         self.eps, self.layer_cl = float(eps), int(layer_cl)
         self.sampler = None
         self.graph = None
+        self._warm = False
 
     # ---- parameters as the reference exposes them ------------------------------------
     @property
@@ -111,7 +128,7 @@ class TrainEngine:
         self.view_adj = [a if isinstance(a, ops.SparseAdj) else ops.SparseAdj(a) for a in (adj1, adj2)]
         for k, a in enumerate(self.view_adj):
             a.cuda(self.dev)
-            self.desc.adj_view[k] = a.graph_struct()
+            self.desc.adj_view[k] = a.graph_struct(self.d)
         self.graph = None  # pointers changed: a captured graph is stale
 
     # ---- stepping ------------------------------------------------------------------------
@@ -158,13 +175,23 @@ class TrainEngine:
     def capture(self):
         """CUDA graph of one step on the resident batch buffer; replay with graph.replay()."""
         torch.cuda.synchronize()
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(2):  # warm-up outside capture (lazy module load, smem attributes)
-                self._enqueue()
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
+        if not self._warm:
+            # warm-up outside capture (lazy module load, smem attributes).  A warm-up IS a training step on whatever
+            # batch_dev holds: parameters, moments and the step counter (Adam bias correction, Philox stream) are
+            # put back afterwards, so capturing never changes the training trajectory.
+            saved = (self.params.clone(), self.m.clone(), self.v.clone(), self.step_dev.clone(), self.losses.clone())
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self._enqueue()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            for dst, src in zip((self.params, self.m, self.v, self.step_dev, self.losses), saved):
+                dst.copy_(src)
+            del saved
+            torch.cuda.synchronize()
+            self._warm = True
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             self._enqueue()

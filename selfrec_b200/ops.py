@@ -46,12 +46,36 @@ def _i32(x, device):
 # ----------------------------------------------------------------------------------------
 # adjacency handle + SpMM
 # ----------------------------------------------------------------------------------------
+def classify_rows(rowptr):
+    """Row classes of the SpMM for a CSR row-pointer tensor (int32, any device): processing order (degree-descending,
+    stable), class sizes, and the chunk lists of the split rows (srb_hub_split in include/selfrec_b200.h).
+    Returns dict(row_order, n_huge, n_vlong, n_long, hub_first, hub_work, n_work)."""
+    rp = rowptr.to(torch.int64)
+    deg = rp[1:] - rp[:-1]
+    order = torch.sort(deg, descending=True, stable=True).indices
+    n_huge = int((deg >= _lib.HUB_MIN_NNZ).sum())
+    n_vlong = int((deg >= VLONG_ROW_NNZ).sum()) - n_huge
+    n_long = int((deg >= LONG_ROW_NNZ).sum()) - n_huge - n_vlong
+    out = dict(row_order=order.to(torch.int32), n_huge=n_huge, n_vlong=n_vlong, n_long=n_long, hub_first=None, hub_work=None, n_work=0)
+    if n_huge:
+        rows = order[:n_huge]
+        nch = (deg[rows] + _lib.HUB_CHUNK - 1) // _lib.HUB_CHUNK
+        first = torch.cumsum(nch, 0) - nch
+        n_work = int(nch.sum())
+        wrow = torch.repeat_interleave(rows, nch)
+        wci = torch.arange(n_work, device=rp.device) - torch.repeat_interleave(first, nch)
+        out.update(hub_first=first.to(torch.int32).contiguous(), hub_work=torch.stack([wrow, wci], 1).to(torch.int32).contiguous(),
+                   n_work=n_work)
+    return out
+
+
 class SparseAdj:
     """Device CSR handle returned by TorchGraphInterface.convert_sparse_mat_to_tensor.
 
     Stands in for the torch COO tensor of base/torch_interface.py:8-13: `.cuda()` uploads
     (identity afterwards) and `torch.sparse.mm(handle, X)` routes to the CUDA SpMM through
-    __torch_function__, differentiable w.r.t. X.
+    __torch_function__, differentiable w.r.t. X.  from_device() wraps a CSR that was assembled
+    on the GPU (srb_graph_assemble: config-5 graphs, SGL's per-epoch views) without a host copy.
     """
 
     def __init__(self, mat):
@@ -63,12 +87,34 @@ class SparseAdj:
             raise SrbError("SparseAdj: nnz must fit in int32")
         self._csr = csr
         self.shape = tuple(csr.shape)
+        self.nnz = int(csr.nnz)
         self.device = torch.device("cpu")
         self.rowptr = self.colidx = self.vals = self.row_order = None
-        self.n_long = 0
-        self.n_vlong = 0
+        self.n_long = self.n_vlong = self.n_huge = self.n_work = 0
+        self.hub_first = self.hub_work = None
+        self._hub_part = {}
         self._t = None  # transposed handle (backward), built lazily
         self._symmetric = None
+
+    @classmethod
+    def from_device(cls, rowptr, colidx, vals, shape, symmetric=None, classes=None):
+        """Wrap device CSR arrays (int32 rowptr [n+1], int32 colidx [nnz], fp32 vals [nnz], columns ascending)."""
+        self = cls.__new__(cls)
+        self._csr = None
+        self.shape = tuple(int(x) for x in shape)
+        self.nnz = int(colidx.numel())
+        self.device = rowptr.device
+        self.rowptr, self.colidx, self.vals = rowptr, colidx, vals
+        self._hub_part = {}
+        self._t = None
+        self._symmetric = symmetric
+        self._set_classes(classify_rows(rowptr) if classes is None else classes)
+        return self
+
+    def _set_classes(self, c):
+        self.row_order = c["row_order"]
+        self.n_huge, self.n_vlong, self.n_long = c["n_huge"], c["n_vlong"], c["n_long"]
+        self.hub_first, self.hub_work, self.n_work = c["hub_first"], c["hub_work"], c["n_work"]
 
     # -- reference-compatible surface -------------------------------------------------
     def cuda(self, device=None):
@@ -76,15 +122,15 @@ class SparseAdj:
         dev = torch.device("cuda", torch.cuda.current_device() if device is None else device) if not isinstance(device, torch.device) else device
         if self.rowptr is not None and self.device == dev:
             return self
+        if self._csr is None:
+            raise SrbError("SparseAdj.from_device handles stay on the device they were built on")
         csr = self._csr
         self.rowptr = torch.from_numpy(csr.indptr.astype(np.int32)).to(dev)
         self.colidx = torch.from_numpy(csr.indices.astype(np.int32)).to(dev)
         self.vals = torch.from_numpy(csr.data.astype(np.float32)).to(dev)
         # long rows first: evens out the tail of the warp-per-row kernel on power-law graphs
-        deg = np.diff(csr.indptr)
-        self.row_order = torch.from_numpy(np.argsort(-deg, kind="stable").astype(np.int32)).to(dev)
-        self.n_vlong = int((deg >= VLONG_ROW_NNZ).sum())                # rows that get a whole CTA in the SpMM
-        self.n_long = int((deg >= LONG_ROW_NNZ).sum()) - self.n_vlong  # rows that get a whole warp
+        self._set_classes(classify_rows(self.rowptr))
+        self._hub_part = {}
         self.device = dev
         return self
 
@@ -98,18 +144,24 @@ class SparseAdj:
         return self.shape if dim is None else self.shape[dim]
 
     def _nnz(self):
-        return int(self._csr.nnz)
+        return self.nnz
+
+    def _host_csr(self):
+        if self._csr is None:
+            import scipy.sparse as sp
+            self._csr = sp.csr_matrix((self.vals.cpu().numpy(), self.colidx.cpu().numpy(), self.rowptr.cpu().numpy()), shape=self.shape)
+        return self._csr
 
     def _indices(self):
-        coo = self._csr.tocoo()
+        coo = self._host_csr().tocoo()
         return torch.from_numpy(np.vstack([coo.row, coo.col]).astype(np.int64)).to(self.device)
 
     def _values(self):
-        return torch.from_numpy(self._csr.tocoo().data.astype(np.float32)).to(self.device)
+        return torch.from_numpy(self._host_csr().tocoo().data.astype(np.float32)).to(self.device)
 
     def is_symmetric(self):
         if self._symmetric is None:
-            a = self._csr
+            a = self._host_csr()
             self._symmetric = a.shape[0] == a.shape[1] and (abs(a - a.T) > 0).nnz == 0
         return self._symmetric
 
@@ -117,7 +169,7 @@ class SparseAdj:
         if self.is_symmetric():
             return self
         if self._t is None:
-            self._t = SparseAdj(self._csr.T.tocsr())
+            self._t = SparseAdj(self._host_csr().T.tocsr())
             self._t._t = self
         if self.rowptr is not None:
             self._t.cuda(self.device)
@@ -129,11 +181,23 @@ class SparseAdj:
             return spmm(args[0], args[1])
         return NotImplemented
 
-    def graph_struct(self):
+    def hub_struct(self, d):
+        """srb_hub_split of this graph for embedding size d (the partial-sum scratch is allocated on first use)."""
+        h = _lib.HubSplit()
+        if self.n_huge:
+            part = self._hub_part.get(d)
+            if part is None:
+                part = self._hub_part[d] = torch.empty((self.n_work, d), device=self.device, dtype=torch.float32)
+            h.n_rows, h.n_work = self.n_huge, self.n_work
+            h.first, h.work, h.part = _p(self.hub_first), _p(self.hub_work), _p(part)
+        return h
+
+    def graph_struct(self, d):
         g = _lib.GraphCsr()
         g.rowptr, g.colidx, g.vals, g.row_order = _p(self.rowptr), _p(self.colidx), _p(self.vals), _p(self.row_order)
         g.n_long_rows = self.n_long
         g.n_vlong_rows = self.n_vlong
+        g.hub = self.hub_struct(d)
         return g
 
 
@@ -151,6 +215,7 @@ def _spmm_raw(adj, x, y=None, **epi):
     desc.rowptr, desc.colidx, desc.vals = _p(adj.rowptr), _p(adj.colidx), _p(adj.vals)
     desc.row_order = _p(adj.row_order)
     desc.n_long_rows, desc.n_vlong_rows = adj.n_long, adj.n_vlong
+    desc.hub = adj.hub_struct(d)
     desc.n_rows, desc.n_cols, desc.d = n_rows, n_cols, d
     desc.X = _p(x)
     desc.Y = _p(y)
@@ -209,6 +274,7 @@ def encoder_forward(adj, e0, n_layers, include_ego, noise=None, eps=0.0, layer_c
     desc = _lib.EncoderDesc()
     desc.rowptr, desc.colidx, desc.vals, desc.row_order = _p(adj.rowptr), _p(adj.colidx), _p(adj.vals), _p(adj.row_order)
     desc.n_long_rows, desc.n_vlong_rows = adj.n_long, adj.n_vlong
+    desc.hub = adj.hub_struct(d)
     desc.n, desc.d, desc.n_layers, desc.include_ego, desc.layer_cl = n, d, n_layers, int(include_ego), int(layer_cl)
     if noise is not None:
         noise = _f32c(noise, "encoder noise")

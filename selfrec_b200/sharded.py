@@ -249,8 +249,8 @@ class ShardedXSimGCL:
         self._nl = torch.zeros(2, device=dev)
         self._gn = [torch.zeros((B, d), device=dev) for _ in range(4)]  # g1 / g2 of the user and item problems
         # batch rows of this rank's block by degree class + bitmap of all batch rows (srb_build_batch_rows)
-        self._brows = torch.zeros(9 * B, dtype=torch.int32, device=dev)
-        self._bcnt = torch.zeros(4, dtype=torch.int32, device=dev)
+        self._brows = torch.zeros(12 * B, dtype=torch.int32, device=dev)
+        self._bcnt = torch.zeros(8, dtype=torch.int32, device=dev)
         self._rmask = torch.zeros((self.N + 31) // 32, dtype=torch.int32, device=dev)
         # the final mean is only read at the batch rows: unless the last layer is the CL view, it is evaluated there only
         self._subset = not (self.model == "XSimGCL" and self.layer_cl == self.L) and self.L >= 1
@@ -315,7 +315,7 @@ class ShardedXSimGCL:
         ops.adam_prepare(self.step_dev, self.scalars, self.lr)
         sh = p.shard
         _lib.check(lib.srb_build_batch_rows(ops._p(self.batch_dev), self.B, self.U, ops._p(p.rowptr), sh.row_begin, sh.n_rows, self.N,
-                                            ops._p(self._brows), ops._p(self._bcnt), ops._p(self._rmask), ops._stream()),
+                                            ops._p(self._brows), ops._p(self._bcnt), ops._p(self._rmask), None, None, 0, ops._stream()),
                    "srb_build_batch_rows")
         self._forward(True, batch_rows_only=self._subset)
         # ---- replicated batch losses on the gathered layers ----
