@@ -539,6 +539,67 @@ typedef struct srb_spmm_sharded_desc {
 
 int srb_spmm_csr_allgather(const srb_spmm_sharded_desc* desc, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Bipartite-sharded training step (selfrec_b200/csrc/sharded.cu).  One process per GPU.
+ * Rank g owns the users [user_bounds[g], user_bounds[g+1]) -- their rows of every [U, d] table stay on that GPU --
+ * and the item tables are replicated; per propagation layer only the item half is exchanged: each rank's partial
+ * product R_g^T X_u is stored by the SpMM epilogue into the staging area of the rank that owns the item slice
+ * (P2P stores, reduce-scatter), the owner adds the partials in rank order, applies the epilogue and stores the
+ * finished rows into every rank's copy (all-gather; one multicast store per row when sym_mc is given).  Item slice
+ * of rank g: [g * I / world, (g+1) * I / world).
+ *   Ru  CSR [n_local_users x n_items]: rows = this rank's users (local ids), columns = item ids
+ *   Rt  CSR [n_items x n_local_users]: its transpose (columns = local user ids); values = the rank's block of the
+ *       normalised adjacency (data/graph.py:10-24)
+ *   sym[q]   base of rank q's symmetric region (torch.distributed._symmetric_memory), sym_bytes each, zero-filled
+ *            once before the first step; item parameters live at srb_shard_layout.item_params inside it
+ *   workspace local, zero-filled once before the first step (it holds the barrier epoch)
+ * Models: LightGCN, SimGCL, XSimGCL (same arithmetic as srb_train_step; noise from the in-kernel Philox stream,
+ * keyed by GLOBAL row id, so a sharded run draws the noise the single-GPU engine draws).  world == 1 is valid.
+ * ------------------------------------------------------------------------------------- */
+typedef struct srb_shard_desc {
+  int32_t model;
+  int32_t world, rank;
+  int32_t n_users, n_items, d, n_layers, batch_cap, layer_cl;
+  float eps, tau, cl_rate, reg;
+  double lr, beta1, beta2;
+  float adam_eps;
+  float l2_div;
+  int32_t noise_mode; /* 0 (LightGCN) or 2 */
+  uint64_t philox_seed;
+  int32_t user_bounds[9]; /* inner bounds multiples of 32 */
+  srb_graph_csr Ru;
+  srb_graph_csr Rt;
+  const int32_t* batch; /* device batch buffer, identical on every rank */
+  float* pu;            /* [n_local_users, d] parameters of the owned users */
+  float* mu;
+  float* vu;
+  float* mi;            /* [n_items, d] Adam moments of the items (only the owned slice is used) */
+  float* vi;
+  int32_t* step_dev;
+  float* scalars;
+  float* losses;        /* [4] rec, l2, cl, total (replicated) */
+  void* sym[8];
+  void* sym_mc;         /* multicast mapping of the symmetric region, or NULL */
+  int64_t sym_bytes;
+  void* workspace;
+  int64_t workspace_bytes;
+} srb_shard_desc;
+
+typedef struct srb_shard_layout {
+  int64_t sym_bytes;       /* size of the symmetric region */
+  int64_t workspace_bytes; /* size of the local workspace */
+  int64_t item_params;     /* byte offset of the [n_items, d] item parameters inside the symmetric region */
+  int64_t item_final;      /* byte offset of the [n_items, d] item output of srb_shard_forward */
+  int64_t ctrl;            /* byte offset inside the workspace of int32 {barrier epoch, peer-timeout flag} */
+} srb_shard_layout;
+
+int srb_shard_plan(int32_t n_users, int32_t n_items, int32_t n_local_users, int32_t d, int32_t batch_cap,
+                     int32_t world, srb_shard_layout* out);
+int srb_shard_step(const srb_shard_desc* desc, void* stream);
+/* clean forward (evaluation / save(), XSimGCL.py:40-41,53-55): out_user [n_local_users, d]; the complete item half
+ * lands in every rank's symmetric region at item_final */
+int srb_shard_forward(const srb_shard_desc* desc, float* out_user, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -117,6 +117,24 @@ class StepDesc(C.Structure):
     ]
 
 
+class ShardDesc(C.Structure):
+    _fields_ = [
+        ("model", C.c_int32), ("world", C.c_int32), ("rank", C.c_int32), ("n_users", C.c_int32), ("n_items", C.c_int32),
+        ("d", C.c_int32), ("n_layers", C.c_int32), ("batch_cap", C.c_int32), ("layer_cl", C.c_int32),
+        ("eps", C.c_float), ("tau", C.c_float), ("cl_rate", C.c_float), ("reg", C.c_float),
+        ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("adam_eps", C.c_float), ("l2_div", C.c_float),
+        ("noise_mode", C.c_int32), ("philox_seed", C.c_uint64), ("user_bounds", C.c_int32 * 9),
+        ("Ru", GraphCsr), ("Rt", GraphCsr), ("batch", VP), ("pu", VP), ("mu", VP), ("vu", VP), ("mi", VP), ("vi", VP),
+        ("step_dev", VP), ("scalars", VP), ("losses", VP), ("sym", VP * 8), ("sym_mc", VP), ("sym_bytes", C.c_int64),
+        ("workspace", VP), ("workspace_bytes", C.c_int64),
+    ]
+
+
+class ShardLayout(C.Structure):
+    _fields_ = [("sym_bytes", C.c_int64), ("workspace_bytes", C.c_int64), ("item_params", C.c_int64), ("item_final", C.c_int64),
+                ("ctrl", C.c_int64)]
+
+
 class SpmmShardedDesc(C.Structure):
     _fields_ = [("local", SpmmDesc), ("row_begin", C.c_int32), ("world", C.c_int32), ("peer_Y", VP * 8), ("peer_sum", VP * 8),
                 ("peer_p", VP * 8)]
@@ -172,6 +190,9 @@ SYMBOLS = {
     "srb_sampler_epoch": (C.c_int64, [VP, C.c_int32, C.c_int32, c_i32p, C.c_int64]),
     "srb_sampler_pairs": (C.c_int64, [VP]),
     "srb_spmm_csr_allgather": (C.c_int, [C.POINTER(SpmmShardedDesc), VP]),
+    "srb_shard_plan": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(ShardLayout)]),
+    "srb_shard_step": (C.c_int, [C.POINTER(ShardDesc), VP]),
+    "srb_shard_forward": (C.c_int, [C.POINTER(ShardDesc), VP, VP]),
 }
 
 _lib = None

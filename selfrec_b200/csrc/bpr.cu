@@ -173,7 +173,11 @@ __global__ void __launch_bounds__(256) scatter_add_rows_kernel(float* dst, const
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int nn = sg.n_dev ? min(*sg.n_dev, sg.n) : sg.n;
   if (r >= nn) return;
-  const int row = sg.rows[r] + sg.row_off;
+  int row = sg.rows[r] + sg.row_off;
+  if (sg.row_hi > sg.row_lo) {  // sharded tables: only the rows this rank owns
+    if (row < sg.row_lo || row >= sg.row_hi) return;
+    row -= sg.row_lo;
+  }
   for (int c = lane * 4; c < D; c += 128) {
     const float4 v = f4_scale(sg.scale, ldg4(sg.src + (size_t)r * D + c));
     atomicAdd(reinterpret_cast<float4*>(dst + (size_t)row * D + c), v);  // red.global.add.v4.f32 (sm_90+)
@@ -332,7 +336,7 @@ extern "C" int srb_scatter_add_rows(float* dst, int32_t d, const float* src, con
   SRB_REQUIRE(n >= 0, "scatter: negative n");
   srb::ScatterSegs segs;
   segs.count = 1;
-  segs.s[0] = {src, rows, n_dev, n, row_off, scale};
+  segs.s[0] = {src, rows, n_dev, n, row_off, scale, 0, 0};
   return srb::scatter_segments(dst, d, segs, (cudaStream_t)stream);
 }
 
@@ -343,7 +347,7 @@ extern "C" int srb_scatter_add_segments(float* dst, int32_t d, int32_t n_segs, c
   segs.count = n_segs;
   for (int q = 0; q < n_segs; ++q) {
     SRB_REQUIRE(in[q].src && in[q].rows && in[q].n >= 0, "scatter: bad segment %d", q);
-    segs.s[q] = {in[q].src, in[q].rows, in[q].n_dev, in[q].n, in[q].row_off, in[q].scale};
+    segs.s[q] = {in[q].src, in[q].rows, in[q].n_dev, in[q].n, in[q].row_off, in[q].scale, 0, 0};
   }
   return srb::scatter_segments(dst, d, segs, (cudaStream_t)stream);
 }

@@ -51,6 +51,7 @@ struct ScatterSeg {
   int32_t n;            // capacity / host count
   int32_t row_off;
   float scale;
+  int32_t row_lo, row_hi;  // optional filter (row_hi > row_lo): only rows[r] + row_off in [row_lo, row_hi), stored at - row_lo
 };
 struct ScatterSegs {
   int count;

@@ -281,7 +281,7 @@ static int run_chain(const srb_step_desc* s, const Ws& w, const Chain& c, bool* 
 }
 
 static ScatterSeg seg(const float* src, const int32_t* rows, const int32_t* n_dev, int n, int row_off, float scale) {
-  ScatterSeg g = {src, rows, n_dev, n, row_off, scale};
+  ScatterSeg g = {src, rows, n_dev, n, row_off, scale, 0, 0};
   return g;
 }
 

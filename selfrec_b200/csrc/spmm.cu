@@ -6,49 +6,16 @@
 //
 // HBM/L2-bound integer + fp32 work: no tensor cores here by design (see the kernel comment
 // for the lane mapping).
-#include "common.cuh"
+#include "spmm_args.cuh"
 
 namespace srb {
 
-struct SpmmArgs {
-  const int32_t* rowptr;
-  const int32_t* colidx;
-  const float* vals;
-  const int32_t* row_order;
-  int32_t n_rows;
-  const int32_t* n_vlong_dev;  // optional device-side class split (see srb_spmm_desc)
-  const uint32_t* col_mask;    // optional: clear bit = X row is zero
-  int32_t n_huge;  // leading entries of row_order that are split into SRB_HUB_CHUNK-sized chunks (spmm_hub_kernel)
-  int32_t n_vlong; // following entries that get a whole CTA
-  int32_t n_long;  // following entries that get a whole warp
-  const int32_t* hub_first;  // [n_huge] first chunk slot of each split row
-  const int32_t* hub_work;   // [n_work][2] (row, chunk index)
-  int32_t n_work;
-  float* hub_part;           // [n_work, D] partial sums of the chunks
-  const float* X;
-  float* Y;
-  const float* extra;
-  float extra_scale;
-  int32_t noise_mode;
-  const float* noise;
-  float eps;
-  uint2 pkey;
-  uint2 poff;
-  const int32_t* pstep;
-  const float* sum_in;
-  float* sum_out;
-  float sum_scale;
-  float* ap;
-  float* am;
-  float* av;
-  const float* ascal;
-  float b2, w1, w2, aeps;  // beta2, 1 - beta1, 1 - beta2 (rounded from double like torch's Python floats)
-  int32_t world;
-  int32_t row_begin;  // global index of local row 0 (epilogue tensors are indexed by global row)
-  float* peer[8];      // layer output -> every rank's buffer
-  float* peer_sum[8];  // running sum  -> every rank's buffer
-  float* peer_p[8];    // updated parameters (Adam epilogue) -> every rank's copy
-};
+// store to another rank's copy: a plain P2P store, or one multimem.st that the NVSwitch replicates into every
+// rank's copy of a multicast-mapped buffer
+__device__ __forceinline__ void st4_peer(float* p, const float4& v, int mc) {
+  if (mc) asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+  else st4(p, v);
+}
 
 // Epilogue of one output row held by a lane group (gl = lane within the group): dense addend, noise,
 // store / peer pushes, running layer sum, Adam.  All lanes of the warp must call it (shuffles);
@@ -59,6 +26,16 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmArgs& a, int row, int gl
   constexpr int HALF = D / 2;
   {
     // ---- epilogue (per lane group = per row) ----
+    if (a.stage_peer[0]) {  // partial product of a sharded item row: hand it to the row's owner, nothing else
+      if (!valid) return;
+      int o = 0;
+#pragma unroll 1
+      while (row >= a.stage_bounds[o + 1]) ++o;
+      float* dst = a.stage_peer[o] + ((size_t)a.stage_rank * a.stage_cap + (row - a.stage_bounds[o])) * D + gl * 4;
+      st4(dst, acc0);
+      st4(dst + HALF, acc1);
+      return;
+    }
     const size_t off = (size_t)(a.row_begin + row) * D + gl * 4;
     float4 y0 = acc0, y1 = acc1;
     if (a.extra && valid) {
@@ -74,7 +51,7 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmArgs& a, int row, int gl
         }
       } else {
         const uint32_t stp = a.pstep ? (uint32_t)*a.pstep : 0u;
-        const uint32_t grow = (uint32_t)(a.row_begin + row);
+        const uint32_t grow = (uint32_t)(a.noise_row_base + a.row_begin + row);
         // counter = (row, column block | view << 16, layer tag, step): (view, step) pairs never share a stream
         const uint32_t vw = a.poff.y << 16;
         const uint4 r0 = philox4x32_10(make_uint4(grow, (uint32_t)gl | vw, a.poff.x, stp), a.pkey);
@@ -99,8 +76,8 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmArgs& a, int row, int gl
     if (a.world > 0 && a.peer[0]) {  // fused all-gather: NVLink P2P stores into every rank's layer buffer
 #pragma unroll 1
       for (int g = 0; g < a.world; ++g) {
-        st4(a.peer[g] + off, y0);
-        st4(a.peer[g] + off + HALF, y1);
+        st4_peer(a.peer[g] + off, y0, a.peer_mc);
+        st4_peer(a.peer[g] + off + HALF, y1, a.peer_mc);
       }
     }
     if (a.sum_out) {
@@ -116,8 +93,8 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmArgs& a, int row, int gl
       if (a.world > 0 && a.peer_sum[0]) {
 #pragma unroll 1
         for (int g = 0; g < a.world; ++g) {
-          st4(a.peer_sum[g] + off, s0);
-          st4(a.peer_sum[g] + off + HALF, s1);
+          st4_peer(a.peer_sum[g] + off, s0, a.peer_mc);
+          st4_peer(a.peer_sum[g] + off + HALF, s1, a.peer_mc);
         }
       }
     }
@@ -143,7 +120,7 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmArgs& a, int row, int gl
         st4(a.av + o2, v4);
         if (a.world > 0 && a.peer_p[0]) {
 #pragma unroll 1
-          for (int g = 0; g < a.world; ++g) st4(a.peer_p[g] + o2, p4);
+          for (int g = 0; g < a.world; ++g) st4_peer(a.peer_p[g] + o2, p4, a.peer_mc);
         }
       }
     }
@@ -409,6 +386,65 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmArgs a) {
   }
 }
 
+// Owner-side reduction of an item slice (bipartite sharding): every rank's item-side product left its partial rows
+// in this rank's staging area; one lane group per slice row adds them in rank order (deterministic, and the only
+// writer of the row) and runs the common epilogue -- noise, layer sum, Adam, and the pushes that hand the finished
+// row to every rank (the all-gather half of the exchange).
+template <int D>
+__global__ void __launch_bounds__(256) reduce_rows_kernel(const SpmmArgs a, const ReduceArgs r) {
+  constexpr int LPR = D / 8;
+  constexpr int RPW = 32 / LPR;
+  constexpr int HALF = D / 2;
+  const int lane = threadIdx.x & 31;
+  const int grp = lane / LPR;
+  const int gl = lane % LPR;
+  const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int n_items = (r.n_slice + RPW - 1) / RPW;
+  for (int item = warp0; item < n_items; item += nwarps) {
+    const int k = item * RPW + grp;
+    const bool valid = k < r.n_slice;
+    float4 acc0 = f4_zero(), acc1 = f4_zero();
+    if (valid) {
+      const float* src = r.stage + (size_t)k * D + gl * 4;
+      const size_t plane = (size_t)r.stage_cap * D;
+#pragma unroll 1
+      for (int q = 0; q < r.world; q += 2) {  // two ranks' partials in flight
+        const bool two = q + 1 < r.world;
+        const float4 p0 = ldg4(src + (size_t)q * plane), p1 = ldg4(src + (size_t)q * plane + HALF);
+        float4 p2 = f4_zero(), p3 = f4_zero();
+        if (two) {
+          p2 = ldg4(src + (size_t)(q + 1) * plane);
+          p3 = ldg4(src + (size_t)(q + 1) * plane + HALF);
+        }
+        acc0 = f4_add(acc0, p0);
+        acc1 = f4_add(acc1, p1);
+        if (two) {
+          acc0 = f4_add(acc0, p2);
+          acc1 = f4_add(acc1, p3);
+        }
+      }
+    }
+    spmm_epilogue<D>(a, r.slice_begin + k, gl, acc0, acc1, valid);
+  }
+}
+
+int launch_reduce_rows(const SpmmArgs& a, const ReduceArgs& r, int d, cudaStream_t st) {
+  if (r.n_slice <= 0) return SRB_OK;
+  const int rpw = 32 / (d / 8);
+  long long blocks = ((long long)(r.n_slice + rpw - 1) / rpw + 7) / 8;
+  const long long cap = (long long)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  switch (d) {
+    case 32: reduce_rows_kernel<32><<<(int)blocks, 256, 0, st>>>(a, r); break;
+    case 64: reduce_rows_kernel<64><<<(int)blocks, 256, 0, st>>>(a, r); break;
+    case 128: reduce_rows_kernel<128><<<(int)blocks, 256, 0, st>>>(a, r); break;
+    default: set_error("reduce_rows: unsupported d=%d (32, 64, 128)", d); return SRB_ERR_ARG;
+  }
+  return post_launch("reduce_rows_kernel");
+}
+
 template <int D>
 static void launch_spmm_d(const SpmmArgs& a, int hub_blocks, int blocks, cudaStream_t st) {
   const bool m = a.col_mask != nullptr;
@@ -423,7 +459,7 @@ static void launch_spmm_d(const SpmmArgs& a, int hub_blocks, int blocks, cudaStr
   else spmm_csr_kernel<D, false><<<blocks, 256, 0, st>>>(a);
 }
 
-static int launch_spmm(const SpmmArgs& a, int d, cudaStream_t st) {
+int launch_spmm(const SpmmArgs& a, int d, cudaStream_t st) {
   if (a.n_rows == 0) return SRB_OK;
   const int threads = 256;
   const int rpw = 32 / (d / 8);
@@ -445,7 +481,7 @@ static int launch_spmm(const SpmmArgs& a, int d, cudaStream_t st) {
   return post_launch("spmm_csr_kernel");
 }
 
-static int fill_args(const srb_spmm_desc* d, SpmmArgs& a) {
+int fill_args(const srb_spmm_desc* d, SpmmArgs& a) {
   SRB_REQUIRE(d != nullptr, "spmm: null desc");
   SRB_REQUIRE(d->rowptr && d->colidx && d->vals && d->X, "spmm: null CSR/X pointer");
   SRB_REQUIRE(d->n_rows >= 0 && d->n_cols >= 0, "spmm: negative shape");
@@ -495,7 +531,11 @@ static int fill_args(const srb_spmm_desc* d, SpmmArgs& a) {
   a.aeps = d->adam_eps;
   a.world = 0;
   a.row_begin = 0;
-  for (int g = 0; g < 8; ++g) a.peer[g] = a.peer_sum[g] = a.peer_p[g] = nullptr;
+  a.noise_row_base = 0;
+  a.peer_mc = 0;
+  a.stage_rank = a.stage_cap = 0;
+  for (int g = 0; g < 8; ++g) a.peer[g] = a.peer_sum[g] = a.peer_p[g] = a.stage_peer[g] = nullptr;
+  for (int g = 0; g < 9; ++g) a.stage_bounds[g] = 0;
   return SRB_OK;
 }
 

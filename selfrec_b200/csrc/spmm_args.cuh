@@ -1,0 +1,70 @@
+// Kernel-argument block of the SpMM family (spmm.cu), shared with the sharded step (sharded.cu).
+#pragma once
+#include "common.cuh"
+
+namespace srb {
+
+struct SpmmArgs {
+  const int32_t* rowptr;
+  const int32_t* colidx;
+  const float* vals;
+  const int32_t* row_order;
+  int32_t n_rows;
+  const int32_t* n_vlong_dev;  // optional device-side class split (see srb_spmm_desc)
+  const uint32_t* col_mask;    // optional: clear bit = X row is zero
+  int32_t n_huge;  // leading entries of row_order that are split into SRB_HUB_CHUNK-sized chunks (spmm_hub_kernel)
+  int32_t n_vlong; // following entries that get a whole CTA
+  int32_t n_long;  // following entries that get a whole warp
+  const int32_t* hub_first;  // [n_huge] first chunk slot of each split row
+  const int32_t* hub_work;   // [n_work][2] (row, chunk index)
+  int32_t n_work;
+  float* hub_part;           // [n_work, D] partial sums of the chunks
+  const float* X;
+  float* Y;
+  const float* extra;
+  float extra_scale;
+  int32_t noise_mode;
+  const float* noise;
+  float eps;
+  uint2 pkey;
+  uint2 poff;
+  const int32_t* pstep;
+  const float* sum_in;
+  float* sum_out;
+  float sum_scale;
+  float* ap;
+  float* am;
+  float* av;
+  const float* ascal;
+  float b2, w1, w2, aeps;  // beta2, 1 - beta1, 1 - beta2 (rounded from double like torch's Python floats)
+  int32_t world;
+  int32_t row_begin;  // global index of local row 0 (epilogue tensors are indexed by global row)
+  float* peer[8];      // layer output -> every rank's buffer
+  float* peer_sum[8];  // running sum  -> every rank's buffer
+  float* peer_p[8];    // updated parameters (Adam epilogue) -> every rank's copy
+  int32_t peer_mc;         // the one peer address is an NVSwitch multicast mapping: stores go out as multimem.st
+  int32_t noise_row_base;  // Philox row id = noise_row_base + row_begin + row (global id of a row of a sharded table)
+  // partial-sum push (bipartite sharding, item-side product): row r of this rank's partial product goes to the
+  // staging area of the rank that owns item r: stage_peer[o] + ((size_t)stage_rank * stage_cap + r - stage_bounds[o]) * D
+  float* stage_peer[8];
+  int32_t stage_bounds[9];
+  int32_t stage_rank;
+  int32_t stage_cap;
+};
+
+// rows of an item slice summed over the ranks' staged partial products (fixed rank order), then the common epilogue
+struct ReduceArgs {
+  const float* stage;  // this rank's staging area: [world][stage_cap, D]
+  int32_t world;
+  int32_t stage_cap;
+  int32_t slice_begin;  // item id of slice row 0 (epilogue tensors are indexed by item id)
+  int32_t n_slice;
+};
+
+int launch_spmm(const SpmmArgs& a, int d, cudaStream_t st);
+int launch_reduce_rows(const SpmmArgs& a, const ReduceArgs& r, int d, cudaStream_t st);
+int fill_args(const srb_spmm_desc* d, SpmmArgs& a);
+
+
+
+}  // namespace srb

@@ -1,0 +1,106 @@
+"""Parity of the bipartite-sharded step against the single-GPU engine, usable inside a run (bench.py prints the
+result in its JSON line, tests assert on it): both engines get the same initial tables, Philox seed and batches,
+so they compute the same trajectory up to fp32 summation order (the sharded item rows are sums of per-rank
+partial sums)."""
+import numpy as np
+
+
+def max_rel(a, b):
+    """max |a - b| / max |b| over a tensor pair (scale-relative: Adam's first steps move every entry by ~lr)."""
+    import torch
+    den = float(b.abs().max().item())
+    return float((a - b).abs().max().item()) / max(den, 1e-30)
+
+
+def sharded_vs_single(model, data, d, L, B, batches, *, steps=3, lr=1e-3, reg=1e-4, seed=7, dev=None, **kw):
+    """Collective over the default process group (or single-process).  Runs `steps` steps of ShardedEngine on all
+    ranks and of TrainEngine on every rank (the reference replica), on batches[k] (device int32 rows).
+    Returns dict(loss_rel, user_rel, item_rel, final_user_rel, final_item_rel, delta_user_rel, ...) -- maxima over steps
+    and ranks."""
+    import torch
+    import torch.distributed as dist
+    from .engine import TrainEngine
+    from .sharded import ShardedEngine
+    dev = torch.device("cuda", torch.cuda.current_device()) if dev is None else dev
+    U, I = int(data.user_num), int(data.item_num)
+    g = torch.Generator(device=dev).manual_seed(1234)
+    iu = torch.empty((U, d), device=dev).uniform_(-0.1, 0.1, generator=g)
+    ii = torch.empty((I, d), device=dev).uniform_(-0.1, 0.1, generator=g)
+    sh = ShardedEngine(model, data, d, L, B, lr, reg, init_user=iu, init_item=ii, philox_seed=seed, device=dev, **kw)
+    ref = TrainEngine(model, data, d, L, B, lr, reg, init_user=iu, init_item=ii, philox_seed=seed, device=dev, **kw)
+    out = dict(loss_rel=0.0, user_rel=0.0, item_rel=0.0, delta_user_rel=0.0, delta_item_rel=0.0)
+    lo, hi = sh.user_lo, sh.user_hi
+    for k in range(steps):
+        w = batches[k % len(batches)]
+        ref.batch_dev.copy_(w)
+        ref.step_resident()
+        sh.step(words_dev=w)
+        torch.cuda.synchronize()
+        la, lb = sh.losses, ref.losses
+        out["loss_rel"] = max(out["loss_rel"], float(((la - lb).abs() / lb.abs().clamp_min(1e-12)).max().item()))
+        out["user_rel"] = max(out["user_rel"], max_rel(sh.user_emb, ref.params[lo:hi]))
+        out["item_rel"] = max(out["item_rel"], max_rel(sh.item_emb, ref.params[U:]))
+        # the update itself (parameters minus initial tables): errors are not hidden behind the size of the table
+        out["delta_user_rel"] = max(out["delta_user_rel"], max_rel(sh.user_emb - iu[lo:hi], ref.params[lo:hi] - iu[lo:hi]))
+        out["delta_item_rel"] = max(out["delta_item_rel"], max_rel(sh.item_emb - ii, ref.params[U:] - ii))
+    fu, fi = sh.forward_clean()
+    ru, ri = ref.forward_clean()
+    torch.cuda.synchronize()
+    out["final_user_rel"] = max_rel(fu, ru[lo:hi])
+    out["final_item_rel"] = max_rel(fi, ri)
+    sh.check_peers()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        t = torch.tensor([out[k] for k in sorted(out)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out = {k: float(v) for k, v in zip(sorted(out), t.tolist())}
+    out["world"] = sh.world
+    out["route"] = "multicast" if sh.use_multicast else ("unicast" if sh.world > 1 else "single")
+    out["steps"] = steps
+    out["max_rel"] = max(out["loss_rel"], out["user_rel"], out["item_rel"], out["final_user_rel"], out["final_item_rel"])
+    del sh, ref
+    torch.cuda.empty_cache()
+    return out
+
+
+def device_batches(data, B, n, seed=0, dev=None):
+    """n batch buffers (srb_sampler_next_batch layout) sampled on the device: uniformly drawn training pairs,
+    uniform negatives re-drawn (a few rounds) while they hit a rated item.  Identical on every rank for a seed."""
+    import torch
+    from . import _lib
+    if hasattr(data, "pairs_dev"):
+        pu, pi = data.pairs_dev
+        rp, ri = data.rated_csr_device()
+    else:
+        dev = torch.device("cuda", torch.cuda.current_device()) if dev is None else dev
+        pu, pi = torch.from_numpy(np.asarray(data.pair_users)).to(dev), torch.from_numpy(np.asarray(data.pair_items)).to(dev)
+        rp, ri = (torch.from_numpy(a).to(dev) for a in data.rated_csr())
+    dev = pu.device
+    g = torch.Generator(device=dev).manual_seed(int(seed))
+    H = _lib.BATCH_HEADER
+    I = int(data.item_num)
+    key = None
+    out = torch.zeros((n, H + 5 * B), dtype=torch.int32, device=dev)
+    for k in range(n):
+        sel = torch.randint(0, pu.numel(), (B,), generator=g, device=dev)
+        u, i = pu[sel].to(torch.int64), pi[sel].to(torch.int64)
+        j = torch.randint(0, I, (B,), generator=g, device=dev)
+        for _ in range(8):  # rejection rounds: is (u, j) a training pair?  (binary search in the user's sorted item list)
+            lo, hi = rp[u].to(torch.int64), rp[u + 1].to(torch.int64)
+            for _s in range(32):
+                mid = (lo + hi) // 2
+                go = (mid < hi) & (ri[mid.clamp(max=ri.numel() - 1)].to(torch.int64) < j)
+                lo = torch.where(go, mid + 1, lo)
+                hi = torch.where(go, hi, mid)
+                if bool((lo >= hi).all()):
+                    break
+            hit = (lo < rp[u + 1].to(torch.int64)) & (ri[lo.clamp(max=ri.numel() - 1)].to(torch.int64) == j)
+            if not bool(hit.any()):
+                break
+            j = torch.where(hit, torch.randint(0, I, (B,), generator=g, device=dev), j)
+        uq, iq = torch.unique(u), torch.unique(i)
+        w = out[k]
+        w[0], w[1], w[2] = B, uq.numel(), iq.numel()
+        w[H:H + B], w[H + B:H + 2 * B], w[H + 2 * B:H + 3 * B] = u.to(torch.int32), i.to(torch.int32), j.to(torch.int32)
+        w[H + 3 * B:H + 3 * B + uq.numel()] = uq.to(torch.int32)
+        w[H + 4 * B:H + 4 * B + iq.numel()] = iq.to(torch.int32)
+    return out

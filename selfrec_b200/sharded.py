@@ -1,17 +1,19 @@
-"""Row-sharded multi-GPU path: one process per GPU, tables split by contiguous,
-nnz-balanced row blocks, the per-layer all-gather fused into the SpMM epilogue.
+"""Bipartite-sharded multi-GPU path: one process per GPU.
 
-Host logic (partitioning, CSR slicing) is plain numpy and is exercised on CPU with a world-size-2
-gloo group (tests/test_sharding_cpu.py).  The device path needs NVLink-connected GPUs: peer
-pointers come from torch.distributed._symmetric_memory, every finished row of a propagated layer
-is stored by the SpMM kernel into each rank's copy (srb_spmm_csr_allgather), and a device-side
-symmetric-memory barrier separates producers from consumers.  torch.distributed (NCCL) is only the
-plumbing: rendezvous and the barrier; the data never goes through a NCCL collective.
+The normalised adjacency is A = [[0, R], [R^T, 0]].  Rank g owns a contiguous, nnz-balanced block of USERS (their
+rows of every [U, d] table never leave the GPU); the ITEM tables are replicated.  Per propagation layer only the
+item half crosses NVLink: every rank's partial product R_g^T X_u is stored by the SpMM epilogue into the staging
+area of the rank owning that item slice, the owner adds the partials, applies the epilogue and stores the finished
+rows into every rank's copy (selfrec_b200/csrc/sharded.cu).  torch.distributed is plumbing only: rendezvous of the
+symmetric-memory region (peer pointers, multicast mapping); no NCCL collective touches the data path.
+
+Host logic here (user partition, block extraction) is plain tensor code that also runs on CPU tensors and is
+exercised with a world-size-2 gloo group in tests/test_sharding_cpu.py.
 """
 import ctypes as C
+import os
 
 import numpy as np
-import scipy.sparse as sp
 
 from . import _lib
 
@@ -27,279 +29,194 @@ def partition_rows(rowptr, world):
     return np.maximum.accumulate(bounds)
 
 
-class LocalShard:
-    """The CSR slice A[R_r, :] of one rank (row pointers rebased, column ids global)."""
-
-    def __init__(self, csr, rank, world, long_row_nnz=64, vlong_row_nnz=256):
-        csr = sp.csr_matrix(csr, dtype=np.float32)
-        csr.sort_indices()
-        self.n = csr.shape[0]
-        self.bounds = partition_rows(csr.indptr, world)
-        self.rank, self.world = rank, world
-        self.row_begin, self.row_end = int(self.bounds[rank]), int(self.bounds[rank + 1])
-        lo, hi = csr.indptr[self.row_begin], csr.indptr[self.row_end]
-        self.rowptr = (csr.indptr[self.row_begin:self.row_end + 1] - lo).astype(np.int32)
-        self.colidx = csr.indices[lo:hi].astype(np.int32)
-        self.vals = csr.data[lo:hi].astype(np.float32)
-        deg = np.diff(self.rowptr)
-        self.row_order = np.argsort(-deg, kind="stable").astype(np.int32)
-        self.n_vlong = int((deg >= vlong_row_nnz).sum())
-        self.n_long = int((deg >= long_row_nnz).sum()) - self.n_vlong
-
-    @property
-    def n_rows(self):
-        return self.row_end - self.row_begin
-
-    def local_csr(self):
-        return sp.csr_matrix((self.vals, self.colidx, self.rowptr), shape=(self.n_rows, self.n))
+def partition_users(user_rowptr, world, align=32):
+    """User blocks with (nearly) equal non-zero counts; inner bounds are multiples of `align` (the bitmap of a
+    block's users must start on a word) and every rank owns at least `align` users."""
+    rp = np.asarray(user_rowptr, dtype=np.int64)
+    U = len(rp) - 1
+    if U < world * align:
+        raise _lib.SrbError(f"{U} users cannot be split over {world} ranks in blocks of >= {align}")
+    b = partition_rows(rp, world)
+    b[1:-1] = (b[1:-1] + align // 2) // align * align
+    for g in range(1, world):  # keep the blocks non-empty after rounding
+        b[g] = min(max(b[g], b[g - 1] + align), (U - (world - g) * align) // align * align)
+    return b
 
 
-class ShardedPropagator:
-    """Device side of one rank: local CSR + symmetric [N, d] buffers every rank can store into."""
-
-    def __init__(self, csr, d, n_buffers, group=None):
-        import torch
-        import torch.distributed as dist
-        import torch.distributed._symmetric_memory as symm
-
-        _lib.require_device()
-        self.torch, self.dist = torch, dist
-        self.group = dist.group.WORLD if group is None else group
-        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
-        if self.world > 8:
-            raise _lib.SrbError("row-sharded path supports up to 8 ranks (one NVSwitch domain)")
-        self.dev = torch.device("cuda", torch.cuda.current_device())
-        self.d = d
-        sh = LocalShard(csr, self.rank, self.world)
-        self.shard = sh
-        self.N = sh.n
-        to = lambda a: torch.from_numpy(a).to(self.dev)
-        self.rowptr, self.colidx, self.vals, self.row_order = to(sh.rowptr), to(sh.colidx), to(sh.vals), to(sh.row_order)
-        self.bufs, self.handles = [], []
-        for _ in range(n_buffers):
-            t = symm.empty((self.N, d), dtype=torch.float32, device=self.dev)
-            h = symm.rendezvous(t, self.group)
-            t.zero_()
-            self.bufs.append(t)
-            self.handles.append(h)
-        # NVSwitch multicast (NVLS): one store to the multicast mapping of a symmetric buffer lands in every
-        # rank's copy, so the SpMM epilogue issues 1 store per row instead of `world` and each GPU's NVLink
-        # egress drops from (world-1)/world of a layer to 1/world of it.  Measured at 2 GPUs it is slower than
-        # unicast (the local copy also travels through the switch: 2984 vs 3281 steps/s), so it is the default
-        # from 4 ranks up; SRB_MULTICAST=0 / 1 forces unicast / multicast.
-        import os
-        self.mc = [int(getattr(h, "multicast_ptr", 0) or 0) for h in self.handles]
-        want = os.environ.get("SRB_MULTICAST", "auto")
-        self.use_mc = self.world > 1 and all(m != 0 for m in self.mc) and (want == "1" or (want == "auto" and self.world >= 4))
-        torch.cuda.synchronize()
-        dist.barrier(self.group)
-
-    def peer_ptrs(self, buf_index):
-        h = self.handles[buf_index]
-        arr = (C.c_void_p * 8)()
-        for g in range(self.world):
-            arr[g] = int(h.buffer_ptrs[g])
-        return arr
-
-    def barrier(self):
-        """Device-side barrier across ranks on the current stream (pushed rows become visible)."""
-        self.handles[0].barrier(channel=0)
-
-    def spmm(self, x, push_y=None, push_sum=None, push_p=None, row_list=None, **epi):
-        """Own rows of A @ x with the fused pushes; x and all epilogue tensors are full [N, d].
-        row_list = (rows, counters, capacity): only the listed local rows (srb_build_batch_rows)."""
-        from . import ops
-        torch = self.torch
-        lib = _lib.load()
-        sd = _lib.SpmmShardedDesc()
-        loc = sd.local
-        loc.rowptr, loc.colidx, loc.vals = ops._p(self.rowptr), ops._p(self.colidx), ops._p(self.vals)
-        loc.row_order, loc.n_long_rows, loc.n_vlong_rows = ops._p(self.row_order), self.shard.n_long, self.shard.n_vlong
-        loc.n_rows, loc.n_cols, loc.d = self.shard.n_rows, self.N, self.d
-        loc.X = ops._p(x)
-        loc.extra_scale, loc.sum_scale = 1.0, 1.0
-        keep = [x]
-        for k, v in epi.items():
-            if isinstance(v, torch.Tensor):
-                keep.append(v)
-                setattr(loc, k, ops._p(v))
-            else:
-                setattr(loc, k, v)
-        if row_list is not None:
-            rows, counters, cap = row_list
-            keep += [rows, counters]
-            loc.row_order, loc.n_rows, loc.n_long_rows, loc.n_vlong_rows = ops._p(rows), cap, 0, 0
-            loc.n_vlong_dev = ops._p(counters)
-        sd.row_begin, sd.world = self.shard.row_begin, (1 if self.use_mc else self.world)
-        for idx, field in ((push_y, "peer_Y"), (push_sum, "peer_sum"), (push_p, "peer_p")):
-            if idx is not None:
-                if self.use_mc:
-                    getattr(sd, field)[0] = self.mc[idx]  # the one "peer" is the multicast address
-                    continue
-                arr = self.peer_ptrs(idx)
-                for g in range(self.world):
-                    getattr(sd, field)[g] = arr[g]
-        _lib.check(lib.srb_spmm_csr_allgather(C.byref(sd), ops._stream()), "srb_spmm_csr_allgather")
+def item_bounds(n_items, world):
+    """Item slice whose reduction rank g owns: [g * I / world, (g + 1) * I / world) (sharded.cu)."""
+    return np.array([g * n_items // world for g in range(world + 1)], dtype=np.int64)
 
 
-class ShardedXSimGCL:
-    """XSimGCL / LightGCN training step on row-sharded tables.
+def extract_blocks(rowptr, colidx, vals, n_users, n_items, ub, ub_end):
+    """Rank-local blocks of the normalised (U+I)^2 adjacency given as CSR tensors (any device):
+    Ru [Ug x I] = A[ub:ub_end, U:] (columns: item ids) and Rt [I x Ug] = A[U:, ub:ub_end] (columns: local user
+    ids).  Returns two (rowptr, colidx, vals) triples of int32 / int32 / fp32 tensors."""
+    import torch
+    U, I = int(n_users), int(n_items)
+    rp = rowptr.to(torch.int64)
+    lo, hi = int(rp[ub]), int(rp[ub_end])
+    ru = ((rp[ub:ub_end + 1] - lo).to(torch.int32), (colidx[lo:hi] - U).to(torch.int32).contiguous(), vals[lo:hi].contiguous())
+    ilo, ihi = int(rp[U]), int(rp[U + I])
+    cols = colidx[ilo:ihi]
+    keep = (cols >= ub) & (cols < ub_end)
+    pref = torch.zeros(ihi - ilo + 1, dtype=torch.int64, device=cols.device)
+    torch.cumsum(keep, 0, out=pref[1:])
+    rt_ptr = pref[rp[U:U + I + 1] - ilo].to(torch.int32)
+    rt = (rt_ptr, (cols[keep] - ub).to(torch.int32).contiguous(), vals[ilo:ihi][keep].contiguous())
+    return ru, rt
 
-    SpMMs and Adam are sharded by rows (each rank computes and pushes its block); the batch losses
-    (BPR, L2, InfoNCE over <= 3B + 2B gathered rows) are replicated on every rank from the gathered
-    layers -- they touch ~2 MB and would cost more to distribute than to recompute.  All ranks hold
-    bit-identical parameters after every step because every rank consumes the same pushed rows.
-    Buffers (symmetric): 0 params, 1/2 layer ping-pong, 3 cl view, 4 final (running layer sum), 5/6 backward
-    ping-pong, 7 batch rows of the final mean (training steps evaluate the last layer on the batch rows only).
-    """
 
-    P, W0, W1, CL, FIN, A0, A1, FINB = range(8)
+class ShardedEngine:
+    """LightGCN / SimGCL / XSimGCL training on bipartite-sharded tables; world == 1 works without torch.distributed.
+
+    Same constructor surface as TrainEngine.  Every rank must feed the SAME batch buffer to step().  Parameters:
+    `user_emb` = this rank's user block [Ug, d] (users user_lo .. user_hi), `item_emb` = the full replicated
+    [I, d] item table.  The in-kernel Philox noise is keyed by global row ids, so a sharded run with the same
+    philox_seed draws the noise the single-GPU TrainEngine draws."""
 
     def __init__(self, model, data, emb_size, n_layers, batch_size, lr, reg, *, eps=0.0, tau=0.2, cl_rate=0.0, layer_cl=0,
-                 l2_div=1.0, init_user=None, init_item=None, group=None):
+                 l2_div=1.0, init_user=None, init_item=None, group=None, philox_seed=0x5EED, device=None, multicast=None):
         import torch
         from . import ops
-        if model not in ("XSimGCL", "LightGCN"):
-            raise _lib.SrbError("sharded engine covers XSimGCL and LightGCN")
-        self.torch, self.ops = torch, ops
-        self.model = model
-        self.prop = ShardedPropagator(data.norm_adj, emb_size, 8, group)
-        p = self.prop
-        self.U, self.I, self.d, self.L, self.B = int(data.user_num), int(data.item_num), int(emb_size), int(n_layers), int(batch_size)
-        self.N = self.U + self.I
-        self.lr, self.reg, self.eps, self.tau, self.cl_rate, self.layer_cl, self.l2_div = lr, reg, eps, tau, cl_rate, layer_cl, l2_div
-        dev = p.dev
+        lib = _lib.require_device()
+        if model not in ("LightGCN", "SimGCL", "XSimGCL"):
+            raise _lib.SrbError("the sharded engine covers LightGCN, SimGCL and XSimGCL")
+        if int(emb_size) not in ops._SUPPORTED_D:
+            raise _lib.SrbError(f"embedding.size {emb_size} is not supported by the CUDA path {ops._SUPPORTED_D}")
+        self.torch, self.ops, self.lib = torch, ops, lib
+        self.model_name = model
+        self.dist = None
+        self.group = None
+        self.rank, self.world = 0, 1
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            self.dist = dist
+            self.group = dist.group.WORLD if group is None else group
+            self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        if self.world > 8:
+            raise _lib.SrbError("the sharded engine supports up to 8 ranks (one NVSwitch domain)")
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        dev = self.dev
+        self.U, self.I, self.d = int(data.user_num), int(data.item_num), int(emb_size)
+        self.N, self.L, self.B = self.U + self.I, int(n_layers), int(batch_size)
+        # ---- graph blocks of this rank ----
+        na = data.norm_adj
+        adj = na if isinstance(na, ops.SparseAdj) else ops.SparseAdj(na)
+        had = adj.rowptr is not None
+        adj.cuda(dev)
+        self.bounds = partition_users(adj.rowptr[: self.U + 1].cpu().numpy(), self.world)
+        self.user_lo, self.user_hi = int(self.bounds[self.rank]), int(self.bounds[self.rank + 1])
+        self.Ug = self.user_hi - self.user_lo
+        ru, rt = extract_blocks(adj.rowptr, adj.colidx, adj.vals, self.U, self.I, self.user_lo, self.user_hi)
+        self.Ru = ops.SparseAdj.from_device(*ru, (self.Ug, self.I), symmetric=False)
+        self.Rt = ops.SparseAdj.from_device(*rt, (self.I, self.Ug), symmetric=False)
+        self.nnzA = adj.nnz
+        if not had and self.world > 1:
+            adj.rowptr = adj.colidx = adj.vals = adj.row_order = None  # the full matrix is not needed on the device any more
+        self.ib = item_bounds(self.I, self.world)
+        # ---- memory ----
+        lay = _lib.ShardLayout()
+        _lib.check(lib.srb_shard_plan(self.U, self.I, self.Ug, self.d, self.B, self.world, C.byref(lay)), "srb_shard_plan")
+        self.layout = lay
+        self.sym_handle = None
+        mc_ptr = 0
+        if self.world > 1:
+            import torch.distributed._symmetric_memory as symm
+            self.sym = symm.empty(int(lay.sym_bytes), dtype=torch.uint8, device=dev)
+            self.sym_handle = symm.rendezvous(self.sym, self.group)
+            peers = [int(p) for p in self.sym_handle.buffer_ptrs]
+            want = os.environ.get("SRB_MULTICAST", "auto") if multicast is None else ("1" if multicast else "0")
+            mc = int(getattr(self.sym_handle, "multicast_ptr", 0) or 0)
+            if mc and (want == "1" or (want == "auto" and self.world >= 4)):
+                mc_ptr = mc
+        else:
+            self.sym = torch.empty(int(lay.sym_bytes), dtype=torch.uint8, device=dev)
+            peers = [self.sym.data_ptr()]
+        self.sym.zero_()
+        self.use_multicast = bool(mc_ptr)
+        self.workspace = torch.zeros(int(lay.workspace_bytes) + 256, dtype=torch.uint8, device=dev)
+        ws_ptr = (self.workspace.data_ptr() + 255) // 256 * 256
+        self._ctrl = self.workspace[ws_ptr - self.workspace.data_ptr() + int(lay.ctrl):][:8].view(torch.int32)
+        nd_i = self.I * self.d
+        self.item_emb = self.sym[int(lay.item_params): int(lay.item_params) + 4 * nd_i].view(torch.float32).view(self.I, self.d)
+        self._item_final = self.sym[int(lay.item_final): int(lay.item_final) + 4 * nd_i].view(torch.float32).view(self.I, self.d)
+        self.user_emb = torch.empty((self.Ug, self.d), device=dev, dtype=torch.float32)
         if init_user is None:
-            g = torch.Generator().manual_seed(0)  # every rank must start from the same table
-            bound_u = (6.0 / (self.U + self.d)) ** 0.5
-            bound_i = (6.0 / (self.I + self.d)) ** 0.5
-            init_user = (torch.rand(self.U, self.d, generator=g) * 2 - 1) * bound_u
-            init_item = (torch.rand(self.I, self.d, generator=g) * 2 - 1) * bound_i
-        self.params = p.bufs[self.P]
-        self.params[: self.U].copy_(torch.as_tensor(init_user))
-        self.params[self.U:].copy_(torch.as_tensor(init_item))
-        self.m = torch.zeros((self.N, self.d), device=dev)
-        self.v = torch.zeros((self.N, self.d), device=dev)
+            if self.N * self.d > (1 << 27):  # config-5 sized tables: drawn on the device, identically on every rank
+                g = torch.Generator(device=dev).manual_seed(int(philox_seed) & 0x7FFFFFFF)
+                bound_u, bound_i = (6.0 / (self.U + self.d)) ** 0.5, (6.0 / (self.I + self.d)) ** 0.5
+                chunk = 1 << 20
+                for lo in range(0, self.U, chunk):  # the same stream on every rank; keep the owned rows
+                    hi = min(self.U, lo + chunk)
+                    blk = torch.empty((hi - lo, self.d), device=dev).uniform_(-bound_u, bound_u, generator=g)
+                    a, b = max(lo, self.user_lo), min(hi, self.user_hi)
+                    if a < b:
+                        self.user_emb[a - self.user_lo: b - self.user_lo].copy_(blk[a - lo: b - lo])
+                self.item_emb.uniform_(-bound_i, bound_i, generator=g)
+            else:
+                g = torch.Generator().manual_seed(int(philox_seed) & 0x7FFFFFFF)  # every rank starts from the same tables
+                init_user = torch.nn.init.xavier_uniform_(torch.empty(self.U, self.d), generator=g)
+                init_item = torch.nn.init.xavier_uniform_(torch.empty(self.I, self.d), generator=g)
+        if init_user is not None:
+            self.user_emb.copy_(torch.as_tensor(init_user)[self.user_lo: self.user_hi])
+            self.item_emb.copy_(torch.as_tensor(init_item))
+        self.mu, self.vu = torch.zeros_like(self.user_emb), torch.zeros_like(self.user_emb)
+        self.mi = torch.zeros((self.I, self.d), device=dev)
+        self.vi = torch.zeros((self.I, self.d), device=dev)
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
         self.scalars = torch.zeros(16, device=dev)
         self.losses = torch.zeros(4, device=dev)
-        self.noise = None
-        self.gd = torch.zeros((self.N, self.d), device=dev)
-        self._alloc_step_buffers()
-        torch.cuda.synchronize()
-        p.dist.barrier(p.group)
-
-    def set_noise_tensor(self, noise):
-        self.noise = self.ops._f32c(noise, "noise")  # [1, L, N, d]
-
-    def _forward(self, perturbed, philox_seed=0x5EED, batch_rows_only=False):
-        p, ops = self.prop, self.ops
-        L = self.L
-        ego = self.model == "LightGCN"
-        inv = 1.0 / (L + 1 if ego else L)
-        x = p.bufs[self.P]
-        for k in range(L):
-            last = k == L - 1
-            is_cl = perturbed and self.layer_cl == k + 1
-            ybuf = self.CL if is_cl else (None if last else (self.W1 if x is p.bufs[self.W0] else self.W0))
-            epi = dict(sum_out=p.bufs[self.FIN], sum_scale=inv if last else 1.0)
-            if k == 0:
-                if ego:
-                    epi["sum_in"] = p.bufs[self.P]
-            else:
-                epi["sum_in"] = p.bufs[self.FIN]
-            if perturbed and self.model == "XSimGCL":
-                epi["eps"] = self.eps
-                if self.noise is not None:
-                    epi.update(noise_mode=1, noise=self.noise[0, k])
-                else:
-                    epi.update(noise_mode=2, philox_seed=philox_seed, philox_offset=0x10 + k, philox_step_dev=self.step_dev)
-            # the running sum only needs to travel once it is final
-            if last and batch_rows_only:
-                # out of place (the list may hold a row twice): final rows go to FINB on every rank
-                epi["sum_out"] = p.bufs[self.FINB]
-                p.spmm(x, push_y=ybuf, push_sum=self.FINB, row_list=(self._brows, self._bcnt, 3 * self.B), **epi)
-            else:
-                p.spmm(x, push_y=ybuf, push_sum=self.FIN if last else None, **epi)
-            p.barrier()
-            if ybuf is not None:
-                x = p.bufs[ybuf]
-        return p.bufs[self.FIN], p.bufs[self.CL]
-
-    def forward_clean(self):
-        fin, _ = self._forward(False)
-        out = fin.clone()
-        return out[: self.U], out[self.U:]
-
-    def _alloc_step_buffers(self):
-        """Everything a step touches is allocated once: a step then makes no allocation and no host read,
-        so it can be captured in a CUDA graph (counts are read by the kernels from the batch header)."""
-        torch, ops, p = self.torch, self.ops, self.prop
-        lib = _lib.load()
-        B, d, U, dev = self.B, self.d, self.U, p.dev
-        self.words = _lib.BATCH_HEADER + 5 * B
+        self.words = _lib.BATCH_HEADER + 5 * self.B
         self.batch_dev = torch.zeros(self.words, dtype=torch.int32, device=dev)
-        w, H = self.batch_dev, _lib.BATCH_HEADER
-        self._cnt = [w[0:1], w[1:2], w[2:3]]                       # b, n_uniq_u, n_uniq_i (device)
-        self._idx = [w[H + q * B: H + (q + 1) * B] for q in range(5)]  # u, i, j, uniq_u, uniq_i (capacity B)
-        self.g_emb = torch.zeros((3, B, d), device=dev)
-        self.g_l2 = torch.zeros((3, B, d), device=dev) if self.model == "LightGCN" else None
-        self._scratch = torch.zeros(8, device=dev)
-        self._bl = torch.zeros(2, device=dev)
-        self._nl = torch.zeros(2, device=dev)
-        self._gn = [torch.zeros((B, d), device=dev) for _ in range(4)]  # g1 / g2 of the user and item problems
-        # batch rows of this rank's block by degree class + bitmap of all batch rows (srb_build_batch_rows)
-        self._brows = torch.zeros(12 * B, dtype=torch.int32, device=dev)
-        self._bcnt = torch.zeros(8, dtype=torch.int32, device=dev)
-        self._rmask = torch.zeros((self.N + 31) // 32, dtype=torch.int32, device=dev)
-        # the final mean is only read at the batch rows: unless the last layer is the CL view, it is evaluated there only
-        self._subset = not (self.model == "XSimGCL" and self.layer_cl == self.L) and self.L >= 1
-        # measured and parity-checked at 2 ranks (unicast pushes, +1 %); with the multicast pushes of >= 4 ranks the
-        # layer exchange is no longer what bounds the step, and the combination has not been run: keep the plain route
-        self._sparse_tricks = not p.use_mc
-        self._subset = self._subset and self._sparse_tricks
-        fin, cl = p.bufs[self.FINB if self._subset else self.FIN], p.bufs[self.CL]
-        u_idx, i_idx, j_idx, uq_u, uq_i = self._idx
-        bd = _lib.BprDesc()
-        bd.emb, bd.n_users, bd.d = ops._p(fin), U, d
-        bd.l2_emb = ops._p(p.bufs[self.P]) if self.model == "LightGCN" else ops._p(fin)
-        bd.u_idx, bd.i_idx, bd.j_idx, bd.b_dev, bd.b = ops._p(u_idx), ops._p(i_idx), ops._p(j_idx), ops._p(self._cnt[0]), B
-        bd.emb_scale, bd.reg, bd.grad_scale = 1.0, self.reg, 1.0
-        bd.l2_terms = 2 if self.model == "XSimGCL" else 3
-        bd.l2_div = self.l2_div
-        bd.losses, bd.g_emb, bd.g_l2, bd.scratch = ops._p(self._bl), ops._p(self.g_emb), ops._p(self.g_l2), ops._p(self._scratch)
-        self._bpr_desc = bd
-        self._nce_desc = None
-        if self.model == "XSimGCL":
-            ws_bytes = lib.srb_infonce_workspace_bytes(B, d, 2)
-            self._nce_ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
-            nd = _lib.InfoNceDesc()
-            nd.n_problems, nd.d, nd.b_cos, nd.temperature = 2, d, 1, float(self.tau)
-            for q, (idx, cnt, off) in enumerate(((uq_u, self._cnt[1], 0), (uq_i, self._cnt[2], U))):
-                pr = nd.prob[q]
-                pr.table1, pr.table2, pr.row_off1, pr.row_off2 = ops._p(fin), ops._p(cl), off, off
-                pr.scale1, pr.scale2 = 1.0, 1.0
-                pr.idx, pr.n_dev, pr.n, pr.weight = ops._p(idx), ops._p(cnt), B, float(self.cl_rate)
-                pr.g1, pr.g2 = ops._p(self._gn[2 * q]), ops._p(self._gn[2 * q + 1])
-                pr.loss = C.c_void_p(self._nl.data_ptr() + 4 * q)
-            nd.workspace, nd.workspace_bytes = ops._p(self._nce_ws), ws_bytes
-            self._nce_desc = nd
-        cm = 1.0 / (self.L + 1 if self.model == "LightGCN" else self.L)
-        b_dev, nu_dev, ni_dev = self._cnt
-        self._final_segs = [(self.g_emb[0], u_idx, b_dev, B, 0, cm), (self.g_emb[1], i_idx, b_dev, B, U, cm),
-                            (self.g_emb[2], j_idx, b_dev, B, U, cm)]
-        self._cl_segs, self._ego_segs = [], []
-        if self.model == "XSimGCL":
-            self._final_segs += [(self._gn[0], uq_u, nu_dev, B, 0, cm), (self._gn[2], uq_i, ni_dev, B, U, cm)]
-            tgt = self._cl_segs if 1 <= self.layer_cl <= self.L else self._ego_segs
-            tgt += [(self._gn[1], uq_u, nu_dev, B, 0, 1.0), (self._gn[3], uq_i, ni_dev, B, U, 1.0)]
-        else:
-            self._ego_segs += [(self.g_l2[0], u_idx, b_dev, B, 0, 1.0), (self.g_l2[1], i_idx, b_dev, B, U, 1.0),
-                               (self.g_l2[2], j_idx, b_dev, B, U, 1.0)]
+        s = _lib.ShardDesc()
+        s.model, s.world, s.rank = _lib.MODEL_IDS[model], self.world, self.rank
+        s.n_users, s.n_items, s.d, s.n_layers, s.batch_cap, s.layer_cl = self.U, self.I, self.d, self.L, self.B, int(layer_cl)
+        s.eps, s.tau, s.cl_rate, s.reg = float(eps), float(tau), float(cl_rate), float(reg)
+        s.lr, s.beta1, s.beta2, s.adam_eps, s.l2_div = float(lr), 0.9, 0.999, 1e-8, float(l2_div)
+        s.noise_mode = 2 if model in ("SimGCL", "XSimGCL") else 0
+        s.philox_seed = int(philox_seed)
+        for g in range(self.world + 1):
+            s.user_bounds[g] = int(self.bounds[g])
+        s.Ru, s.Rt = self.Ru.graph_struct(self.d), self.Rt.graph_struct(self.d)
+        p = ops._p
+        s.batch, s.pu, s.mu, s.vu, s.mi, s.vi = p(self.batch_dev), p(self.user_emb), p(self.mu), p(self.vu), p(self.mi), p(self.vi)
+        s.step_dev, s.scalars, s.losses = p(self.step_dev), p(self.scalars), p(self.losses)
+        for g in range(self.world):
+            s.sym[g] = peers[g]
+        s.sym_mc = mc_ptr or None
+        s.sym_bytes = int(lay.sym_bytes)
+        s.workspace, s.workspace_bytes = C.c_void_p(ws_ptr), int(lay.workspace_bytes)
+        self.desc = s
+        self.graph = None
+        self._warm = False
+        torch.cuda.synchronize()
+        self._host_barrier()
+
+    # ---- plumbing ------------------------------------------------------------------------
+    def _host_barrier(self):
+        if self.dist is not None and self.world > 1:
+            self.dist.barrier(self.group)
+
+    def check_peers(self):
+        """Raise if a device-side barrier ever timed out (a peer died or fell out of step)."""
+        if int(self._ctrl[1].item()) != 0:
+            raise _lib.SrbError("sharded step: a peer rank did not reach a device-side barrier in time")
+
+    def nvlink_bytes_per_layer(self):
+        """Bytes this rank sends per propagation layer: the partial rows it hands to the other slices' owners plus
+        the finished rows of its own slice (one multicast store, or one store per peer)."""
+        if self.world == 1:
+            return 0
+        own = int(self.ib[self.rank + 1] - self.ib[self.rank]) * self.d * 4
+        part = self.I * self.d * 4 - own
+        return part + own * (1 if self.use_multicast else self.world - 1)
+
+    # ---- stepping ------------------------------------------------------------------------
+    def _enqueue(self):
+        _lib.check(self.lib.srb_shard_step(C.byref(self.desc), self.ops._stream()), "srb_shard_step")
 
     def step(self, words=None, words_dev=None):
-        """One training step; the batch buffer (srb_sampler_next_batch layout) must be the same on all ranks.
-        words: host buffer (copied to the device), or words_dev: the buffer already resident on the device."""
         torch = self.torch
         if words_dev is not None:
             self.batch_dev.copy_(words_dev, non_blocking=True)
@@ -308,52 +225,55 @@ class ShardedXSimGCL:
         self.step_resident()
 
     def step_resident(self):
-        """Step on whatever self.batch_dev holds: no allocation, no host read (CUDA-graph capturable)."""
-        torch, ops, p = self.torch, self.ops, self.prop
-        lib = _lib.load()
-        L = self.L
-        ops.adam_prepare(self.step_dev, self.scalars, self.lr)
-        sh = p.shard
-        _lib.check(lib.srb_build_batch_rows(ops._p(self.batch_dev), self.B, self.U, ops._p(p.rowptr), sh.row_begin, sh.n_rows, self.N,
-                                            ops._p(self._brows), ops._p(self._bcnt), ops._p(self._rmask), None, None, 0, ops._stream()),
-                   "srb_build_batch_rows")
-        self._forward(True, batch_rows_only=self._subset)
-        # ---- replicated batch losses on the gathered layers ----
-        _lib.check(lib.srb_bpr_l2_fwd_bwd(C.byref(self._bpr_desc), ops._stream()), "srb_bpr_l2_fwd_bwd")
-        if self._nce_desc is not None:
-            _lib.check(lib.srb_infonce_fwd_bwd(C.byref(self._nce_desc), ops._stream()), "srb_infonce_fwd_bwd")
-        # ---- Horner backward, rows sharded, every level pushed to all ranks ----
-        final_segs, cl_segs, ego_segs = self._final_segs, self._cl_segs, self._ego_segs
-        acc = p.bufs[self.A0]
-        acc.zero_()
-        ops.scatter_add_segments(acc, final_segs + (cl_segs if self.layer_cl == L else []))
-        x_idx = self.A0
-        for k in range(L - 1, 0, -1):
-            y_idx = self.A1 if x_idx == self.A0 else self.A0
-            # the seed of the chain is non-zero at the batch rows only: the first product skips every other column
-            p.spmm(p.bufs[x_idx], push_y=y_idx, **(dict(col_mask=self._rmask) if (k == L - 1 and self._sparse_tricks) else {}))
-            p.barrier()
-            # replicated: every rank adds the same sparse rows to its copy
-            ops.scatter_add_segments(p.bufs[y_idx], final_segs + (cl_segs if self.layer_cl == k else []))
-            x_idx = y_idx
-        extra = None
-        if self.model == "LightGCN" or ego_segs:
-            self.gd.zero_()
-            ops.scatter_add_segments(self.gd, (final_segs if self.model == "LightGCN" else []) + ego_segs)
-            extra = self.gd
-        epi = dict(adam_p=p.bufs[self.P], adam_m=self.m, adam_v=self.v, adam_scalars=self.scalars, beta1=0.9, beta2=0.999, adam_eps=1e-8)
-        if extra is not None:
-            epi["extra"] = extra
-        if L == 1 and self._sparse_tricks:
-            epi["col_mask"] = self._rmask
-        p.spmm(p.bufs[x_idx], push_p=self.P, **epi)
-        p.barrier()
-        ls = self.losses
-        ls[0:2].copy_(self._bl)
-        if self._nce_desc is not None:
-            torch.add(self._nl[0:1], self._nl[1:2], out=ls[2:3])
-            ls[2:3].mul_(self.cl_rate)
+        if self.graph is not None:
+            self.graph.replay()
         else:
-            ls[2:3].zero_()
-        torch.add(ls[0:1], ls[1:2], out=ls[3:4])
-        ls[3:4].add_(ls[2:3])
+            self._enqueue()
+
+    def capture(self):
+        """CUDA graph of one step (device-side barriers included).  Collective: every rank must call it."""
+        torch = self.torch
+        torch.cuda.synchronize()
+        state = (self.user_emb, self.item_emb, self.mu, self.vu, self.mi, self.vi, self.step_dev, self.losses)
+        if not self._warm:  # a warm-up is a real step: put the trajectory back afterwards (all ranks do the same)
+            saved = [t.clone() for t in state]
+            self._host_barrier()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._enqueue()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            self._host_barrier()
+            for dst, src in zip(state, saved):
+                dst.copy_(src)
+            del saved
+            torch.cuda.synchronize()
+            self._host_barrier()
+            self._warm = True
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._enqueue()
+        self.graph = g
+        self._host_barrier()
+        return g
+
+    # ---- inference -------------------------------------------------------------------------
+    def forward_clean(self):
+        """Clean forward -> (final embeddings of this rank's users [Ug, d], final item embeddings [I, d])."""
+        torch = self.torch
+        out_u = torch.empty_like(self.user_emb)
+        _lib.check(self.lib.srb_shard_forward(C.byref(self.desc), self.ops._p(out_u), self.ops._stream()), "srb_shard_forward")
+        return out_u, self._item_final.clone()
+
+    def all_user_rows(self, local):
+        """[U, d] table from every rank's [Ug, d] block (test / evaluation plumbing: one NCCL all_gather)."""
+        torch = self.torch
+        if self.world == 1:
+            return local.clone()
+        sizes = [int(self.bounds[g + 1] - self.bounds[g]) for g in range(self.world)]
+        pad = torch.zeros((max(sizes), self.d), device=self.dev)
+        pad[: self.Ug].copy_(local)
+        outs = [torch.empty_like(pad) for _ in range(self.world)]
+        self.dist.all_gather(outs, pad, group=self.group)
+        return torch.cat([o[:n] for o, n in zip(outs, sizes)], 0)
