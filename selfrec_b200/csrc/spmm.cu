@@ -10,6 +10,8 @@
 
 namespace srb {
 
+__device__ __forceinline__ void st4_cs(float* p, const float4& v) { __stcs(reinterpret_cast<float4*>(p), v); }
+
 // store to another rank's copy: a plain P2P store, or one multimem.st that the NVSwitch replicates into every
 // rank's copy of a multicast-mapped buffer
 __device__ __forceinline__ void st4_peer(float* p, const float4& v, int mc) {
@@ -69,9 +71,9 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmArgs& a, int row, int gl
 #undef SRB_PERT
     }
     if (!valid) return;
-    if (a.Y) {
-      st4(a.Y + off, y0);
-      st4(a.Y + off + HALF, y1);
+    if (a.Y) {  // written once, read (randomly) by the NEXT product: streaming stores
+      st4_cs(a.Y + off, y0);
+      st4_cs(a.Y + off + HALF, y1);
     }
     if (a.world > 0 && a.peer[0]) {  // fused all-gather: NVLink P2P stores into every rank's layer buffer
 #pragma unroll 1
@@ -88,8 +90,8 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmArgs& a, int row, int gl
       }
       s0 = f4_scale(a.sum_scale, s0);
       s1 = f4_scale(a.sum_scale, s1);
-      st4(a.sum_out + off, s0);
-      st4(a.sum_out + off + HALF, s1);
+      st4_cs(a.sum_out + off, s0);
+      st4_cs(a.sum_out + off + HALF, s1);
       if (a.world > 0 && a.peer_sum[0]) {
 #pragma unroll 1
         for (int g = 0; g < a.world; ++g) {
@@ -106,8 +108,8 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmArgs& a, int row, int gl
         const size_t o2 = off + h * HALF;
         const float4 g = h ? y1 : y0;
         float4 p4 = *reinterpret_cast<const float4*>(a.ap + o2);
-        float4 m = *reinterpret_cast<const float4*>(a.am + o2);
-        float4 v4 = *reinterpret_cast<const float4*>(a.av + o2);
+        float4 m = __ldcs(reinterpret_cast<const float4*>(a.am + o2));
+        float4 v4 = __ldcs(reinterpret_cast<const float4*>(a.av + o2));
 #define SRB_ADAM1(F)                                          \
   m.F = m.F + a.w1 * (g.F - m.F);                             \
   v4.F = v4.F * a.b2;                                         \
@@ -116,8 +118,8 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmArgs& a, int row, int gl
         SRB_ADAM1(x) SRB_ADAM1(y) SRB_ADAM1(z) SRB_ADAM1(w)
 #undef SRB_ADAM1
         st4(a.ap + o2, p4);
-        st4(a.am + o2, m);
-        st4(a.av + o2, v4);
+        st4_cs(a.am + o2, m);
+        st4_cs(a.av + o2, v4);
         if (a.world > 0 && a.peer_p[0]) {
 #pragma unroll 1
           for (int g = 0; g < a.world; ++g) st4_peer(a.peer_p[g] + o2, p4, a.peer_mc);
@@ -153,8 +155,8 @@ __device__ __forceinline__ void spmm_gather(const SpmmArgs& a, int p, int end, i
   float v = 0.f;
   bool hit = false;
   if (p + gl < end) {
-    c = __ldg(a.colidx + p + gl);
-    v = __ldg(a.vals + p + gl);
+    c = __ldcs(a.colidx + p + gl);  // the CSR arrays are read once per product: evict-first, so that they do not push
+    v = __ldcs(a.vals + p + gl);    // gathered X rows out of L2 (at config-5 size the product is bound by those re-reads)
     if (masked) hit = (__ldg(a.col_mask + (c >> 5)) >> (c & 31)) & 1u;
   }
   while (__any_sync(SRB_FULL_MASK, p < end)) {
@@ -162,8 +164,8 @@ __device__ __forceinline__ void spmm_gather(const SpmmArgs& a, int p, int end, i
     float vn = 0.f;
     bool hitn = false;
     if (p + stride + gl < end) {  // prefetch the next iteration's pair
-      cn = __ldg(a.colidx + p + stride + gl);
-      vn = __ldg(a.vals + p + stride + gl);
+      cn = __ldcs(a.colidx + p + stride + gl);
+      vn = __ldcs(a.vals + p + stride + gl);
       if (masked) hitn = (__ldg(a.col_mask + (cn >> 5)) >> (cn & 31)) & 1u;
     }
     if (!masked) {

@@ -17,3 +17,13 @@ class LightGCN(FusedGraphModel):
 
     def _log_line(self, epoch, n, losses):
         print("training:", epoch + 1, "batch", n, "batch_loss:", losses[3])
+
+
+from ._common import OpLevelEncoder  # noqa: E402
+
+
+class LGCN_Encoder(OpLevelEncoder):
+    """`from model.graph.LightGCN import LGCN_Encoder` (DirectAU.py:7, SelfCF.py:6) keeps resolving after install()."""
+
+    def __init__(self, data, emb_size, n_layers):
+        super().__init__(data, emb_size, n_layers)

@@ -13,3 +13,13 @@ class MF(FusedGraphModel):
 
     def _log_line(self, epoch, n, losses):
         print("training:", epoch + 1, "batch", n, "batch_loss:", losses[3])
+
+
+from ._common import OpLevelEncoder  # noqa: E402
+
+
+class Matrix_Factorization(OpLevelEncoder):
+    """`from model.graph.MF import Matrix_Factorization` (DirectAU.py:6) keeps resolving after install()."""
+
+    def __init__(self, data, emb_size):
+        super().__init__(data, emb_size, 0)

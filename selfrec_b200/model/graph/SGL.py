@@ -4,7 +4,7 @@ Per epoch two augmented graphs (SGL.py:27-29, via GraphAugmentor + convert_to_la
 three encoders per step (clean + 2 views), one InfoNCE over cat(users, items) (SGL.py:120-125).
 The reference's `aug_type==0 or 1` test is always true (SGL.py:81), so every aug_type yields
 a single graph per view; that behaviour is kept."""
-from ...data.augmentor import GraphAugmentor
+from ...data.augmentor import sample_range
 from ._common import FusedGraphModel
 
 
@@ -22,12 +22,33 @@ class SGL(FusedGraphModel):
         self.temp = float(args["temp"])
         self._make_engine(self.n_layers, tau=self.temp, cl_rate=self.cl_rate)
 
+    def _bipartite(self):
+        if getattr(self, "_bip", None) is None:
+            from ...data.device_graph import DeviceBipartite
+            self._bip = DeviceBipartite.from_interaction_mat(self.data.interaction_mat, self.engine.dev)
+        return self._bip
+
     def random_graph_augment(self):
-        if self.aug_type == 0:
-            dropped = GraphAugmentor.node_dropout(self.data.interaction_mat, self.drop_rate)
-        else:
-            dropped = GraphAugmentor.edge_dropout(self.data.interaction_mat, self.drop_rate)
-        return self.data.convert_to_laplacian_mat(dropped)
+        """One augmented, re-normalised graph (SGL.py:89-96) as a device CSR.  The draw is CPython's random.sample
+        stream (GraphAugmentor's, natively: sample_range); only the kept positions travel to the GPU, where
+        srb_graph_assemble builds D^-1/2 A D^-1/2 bit-identically to the scipy route (data/ui_graph.py:58-65,
+        data/graph.py:10-24)."""
+        import torch
+        bip = self._bipartite()
+        if self.aug_type == 0:  # node dropout (augmentor.py:11-27): users first, then items, like the reference draws
+            n_u, n_i = bip.U, bip.I
+            du = sample_range(n_u, int(n_u * self.drop_rate))
+            di = sample_range(n_i, int(n_i * self.drop_rate))
+            ku = torch.ones(n_u, dtype=torch.uint8, device=bip.dev)
+            ki = torch.ones(n_i, dtype=torch.uint8, device=bip.dev)
+            ku[torch.from_numpy(du).to(bip.dev)] = 0
+            ki[torch.from_numpy(di).to(bip.dev)] = 0
+            if getattr(self, "_ui_row", None) is None:
+                self._ui_row = torch.repeat_interleave(torch.arange(n_u, device=bip.dev), (bip.ui_ptr[1:] - bip.ui_ptr[:-1]).long())
+            flags = ku[self._ui_row] & ki[bip.ui_col.long()]
+            return bip.assemble(keep_flags=flags, reset_weights=True)
+        keep = sample_range(bip.nnz, int(bip.nnz * (1 - self.drop_rate)))  # edge dropout (augmentor.py:30-40)
+        return bip.assemble(keep_idx=keep, reset_weights=True)
 
     def _epoch_prologue(self, epoch):
         self.engine.set_view_graphs(self.random_graph_augment(), self.random_graph_augment())

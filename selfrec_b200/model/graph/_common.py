@@ -75,3 +75,40 @@ class FusedGraphModel(GraphRecommender):
         # never calls this -- it uses the fused scoring + top-k kernel.
         from ... import ops
         return ops.score_rows(self.user_emb, self.item_emb, [u])[0].cpu().numpy()
+
+
+class OpLevelEncoder(nn.Module):
+    """Autograd-visible encoder on the drop-in ops, for the reference models that import another model's encoder
+    class (`from model.graph.LightGCN import LGCN_Encoder`: DirectAU.py:7, SelfCF.py:6; `from model.graph.MF import
+    Matrix_Factorization`: DirectAU.py:6).  Same attributes the callers touch (data, latent_size, layers, norm_adj,
+    embedding_dict, sparse_norm_adj) and the same forward() contract: (user embeddings, item embeddings), the mean of
+    the ego layer and `layers` propagated ones (LightGCN.py:68-78); zero layers is matrix factorisation (MF.py:52-53).
+    Propagation is torch.sparse.mm on the SparseAdj handle, i.e. the CUDA SpMM, differentiable w.r.t. the table."""
+
+    def __init__(self, data, emb_size, n_layers=0):
+        super().__init__()
+        from ...base.torch_interface import TorchGraphInterface
+        self.data = data
+        self.latent_size = emb_size
+        self.layers = n_layers
+        init = nn.init.xavier_uniform_  # users first, then items: the reference's draw order (LightGCN.py:60-66)
+        self.embedding_dict = nn.ParameterDict({
+            "user_emb": nn.Parameter(init(torch.empty(data.user_num, emb_size))),
+            "item_emb": nn.Parameter(init(torch.empty(data.item_num, emb_size))),
+        })
+        if n_layers > 0:
+            self.norm_adj = data.norm_adj
+            self.sparse_norm_adj = TorchGraphInterface.convert_sparse_mat_to_tensor(self.norm_adj).cuda()
+
+    def forward(self):
+        pd = self.embedding_dict
+        if self.layers == 0:
+            return pd["user_emb"], pd["item_emb"]
+        x = torch.cat([pd["user_emb"], pd["item_emb"]], 0)
+        total = x
+        for _ in range(self.layers):
+            x = torch.sparse.mm(self.sparse_norm_adj, x)
+            total = total + x
+        out = total / float(self.layers + 1)
+        n_u = self.data.user_num
+        return out[:n_u], out[n_u:]

@@ -35,11 +35,12 @@ def main():
         for model, d, L, kw in cases:
             for mc in routes:
                 r = sharded_vs_single(model, data, d, L, B, batches, steps=3, multicast=mc, **kw)
-                good = r["max_rel"] <= TOL and r["delta_user_rel"] <= 2e-3 and r["delta_item_rel"] <= 2e-3
+                good = r["max_rel"] <= TOL and r["upd_off_frac"] <= 0.02 and max(r["user_rel"], r["item_rel"]) <= 0.05
                 if rank == 0:
                     print(f"{gname} {model} d={d} L={L} route={r['route']}: max_rel {r['max_rel']:.2e} "
-                          f"(loss {r['loss_rel']:.1e} user {r['user_rel']:.1e} item {r['item_rel']:.1e} final {r['final_user_rel']:.1e}/"
-                          f"{r['final_item_rel']:.1e} delta {r['delta_user_rel']:.1e}/{r['delta_item_rel']:.1e}) {'ok' if good else 'FAIL'}",
+                          f"(loss {r['loss_rel']:.1e} m {r['m_user_rel']:.1e}/{r['m_item_rel']:.1e} v {r['v_user_rel']:.1e}/{r['v_item_rel']:.1e} "
+                          f"final {r['final_user_rel']:.1e}/{r['final_item_rel']:.1e} params {r['user_rel']:.1e}/{r['item_rel']:.1e} "
+                          f"updates off {r['upd_off_frac']:.1e}) {'ok' if good else 'FAIL'}",
                           flush=True)
                 ok = ok and good
     if rank == 0:

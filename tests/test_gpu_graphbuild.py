@@ -163,3 +163,27 @@ def test_engine_step_on_device_built_zipf_graph_vs_oracle(torch_cuda, orc, model
     g = ref["grad"]
     big = np.abs(g) > 1e-3 * np.abs(g).max()
     assert not (bad & big).any()
+
+
+@pytest.mark.parametrize("aug_type", [0, 1])
+def test_sgl_model_views_device_route_equals_reference_route(torch_cuda, tiny_conf, tiny_triples, in_tmp_cwd, aug_type):
+    """SGL.random_graph_augment (fused model): node dropout (aug_type 0) and edge dropout (1) built on the device equal
+    GraphAugmentor + convert_to_laplacian_mat on the host, draw for draw (same `random` stream, same final state)."""
+    from selfrec_b200.data.augmentor import GraphAugmentor
+    from selfrec_b200.model.graph.SGL import SGL
+    train, test = tiny_triples
+    m = SGL(tiny_conf("SGL", {"n_layer": 2, "lambda": 0.1, "drop_rate": 0.2, "aug_type": aug_type, "temp": 0.2}),
+            [list(t) for t in train], [list(t) for t in test])
+    random.seed(77)
+    drop = GraphAugmentor.node_dropout if aug_type == 0 else GraphAugmentor.edge_dropout
+    ref = [m.data.convert_to_laplacian_mat(drop(m.data.interaction_mat, 0.2)) for _ in range(2)]
+    state = random.getstate()
+    random.seed(77)
+    got = [m.random_graph_augment() for _ in range(2)]
+    assert random.getstate() == state
+    for a, r in zip(got, ref):
+        r = sp.csr_matrix(r)
+        r.eliminate_zeros()
+        _same_csr(a, r)
+    m._epoch_prologue(0)  # and the engine accepts the device handles
+    assert m.engine.view_adj[0].rowptr.is_cuda

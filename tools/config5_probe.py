@@ -42,7 +42,7 @@ def main():
     ap.add_argument("shape", nargs="?", default="synthetic-2M")
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--model", default="SimGCL")
-    ap.add_argument("--d", type=int, default=128)
+    ap.add_argument("--dim", type=int, default=128)
     ap.add_argument("--layers", type=int, default=3)
     ap.add_argument("--alpha", type=float, default=1.1)
     ap.add_argument("--eager", action="store_true")
@@ -53,7 +53,7 @@ def main():
     from selfrec_b200.engine import TrainEngine
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
-    rec = {"shape": args.shape, "model": args.model, "d": args.d, "alpha": args.alpha}
+    rec = {"shape": args.shape, "model": args.model, "d": args.dim, "alpha": args.alpha}
     t0 = time.perf_counter()
     shape = synth.SHAPES[args.shape] if args.shape in synth.SHAPES else tuple(int(x) for x in args.shape.split("x"))
     pu, pi = synth.make_pairs_device(*shape, seed=0, alpha=args.alpha, device=dev)
@@ -71,7 +71,7 @@ def main():
     torch.cuda.empty_cache()
     rec["mem_after_build_gb"] = torch.cuda.memory_allocated() / 1e9
     # ---- SpMM alone ----
-    N, d = adj.shape[0], args.d
+    N, d = adj.shape[0], args.dim
     x = torch.randn(N, d, device=dev)
     y = torch.empty_like(x)
     for _ in range(2):

@@ -17,7 +17,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("shape", nargs="?", default="synthetic-2M")
     ap.add_argument("--model", default="SimGCL")
-    ap.add_argument("--d", type=int, default=128)
+    ap.add_argument("--dim", type=int, default=128)
     ap.add_argument("--layers", type=int, default=3)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--alpha", type=float, default=1.1)
@@ -38,7 +38,7 @@ def main():
     build.build()
     from selfrec_b200.shard_check import device_batches, sharded_vs_single
     from selfrec_b200.sharded import ShardedEngine
-    rec = {"shape": args.shape, "model": args.model, "d": args.d, "world": world}
+    rec = {"shape": args.shape, "model": args.model, "d": args.dim, "world": world}
     t0 = time.perf_counter()
     if args.shape in ("yelp2018", "amazon-kindle", "douban-book"):
         data = synth.make_interaction(args.shape, seed=0)
@@ -57,9 +57,9 @@ def main():
             fu = float((bip.iu_col < K).float().mean().item())
             rec[f"share_cols_lt_{K}"] = {"item_cols_of_user_rows": fi, "user_cols_of_item_rows": fu}
     if args.parity:
-        rec["parity"] = sharded_vs_single(args.model, data, args.d, args.layers, B, pool, steps=3, dev=dev, **kw)
+        rec["parity"] = sharded_vs_single(args.model, data, args.dim, args.layers, B, pool, steps=3, dev=dev, **kw)
         torch.cuda.empty_cache()
-    sh = ShardedEngine(args.model, data, args.d, args.layers, B, 1e-3, 1e-4, device=dev, **kw)
+    sh = ShardedEngine(args.model, data, args.dim, args.layers, B, 1e-3, 1e-4, device=dev, **kw)
     rec["mem_gb"] = torch.cuda.memory_allocated() / 1e9
     rec["nvlink_bytes_per_layer_out"] = sh.nvlink_bytes_per_layer()
     rec["route"] = "multicast" if sh.use_multicast else "unicast"
