@@ -57,12 +57,27 @@ int srb_device_ok(void);
  * from n_vlong_dev[0] (rows) and n_vlong_dev[4] (chunks). */
 #define SRB_HUB_CHUNK 2048
 #define SRB_HUB_MIN_NNZ 4096
+#define SRB_HUB_WARP_SEG 256
 typedef struct srb_hub_split {
   int32_t n_rows;
   int32_t n_work;
   const int32_t* first; /* [n_rows] */
   const int32_t* work;  /* [n_work][2] */
   float* part;          /* [n_work, d] scratch (one product at a time per graph) */
+  /* Column-blocked variant of the static lists (optional; seg != NULL selects it).  At config-5 size the split rows
+   * hold ~40 % of the non-zeros and their gathers miss L2 (the X table is 6 GB): cutting every split row at column-block
+   * boundaries (a block of X rows ~ 32 MB) and processing ALL rows' segments of one block before the next keeps that
+   * block of X in L2, so it is read from HBM once per product instead of once per row.
+   *   seg[w] = (begin, end) CSR positions of segment w; a row's segments are consecutive slots (first[r], seg_cnt[r]);
+   *   n_work = number of segments (capacity of part);
+   *   order_cta / order_warp: segment ids in processing order (column block, then row): segments longer than
+   *   SRB_HUB_WARP_SEG non-zeros take a CTA each, the others a warp each. */
+  const int32_t* seg;       /* [n_work][2] */
+  const int32_t* seg_cnt;   /* [n_rows] */
+  const int32_t* order_cta;
+  const int32_t* order_warp;
+  int32_t n_cta;
+  int32_t n_warp;
 } srb_hub_split;
 
 typedef struct srb_spmm_desc {
@@ -516,6 +531,15 @@ int srb_sampler_next_batch_negs(srb_sampler* s, int32_t batch_size, int32_t n_ne
 int64_t srb_sampler_epoch(srb_sampler* s, int32_t batch_size, int32_t batch_cap, int32_t* out,
                           int64_t out_words);
 int64_t srb_sampler_pairs(const srb_sampler* s);
+/* Sample-ahead ring: after srb_sampler_begin_epoch, one native thread fills up to `depth` batches ahead of the
+ * consumer (same layout and -- the producer being the only reader of the MT19937 state -- the same batches as
+ * srb_sampler_next_batch would return).  srb_sampler_ring_pop blocks for the next batch and returns its size, 0 at
+ * the end of the epoch.  srb_sampler_ring_stop joins the producer and puts the generator back to the state after the
+ * last batch the caller popped (batches sampled ahead but never read are un-drawn), so srb_sampler_get_state returns
+ * the reference's stream position whenever the ring is stopped. */
+int srb_sampler_ring_start(srb_sampler* s, int32_t batch_size, int32_t batch_cap, int32_t depth);
+int srb_sampler_ring_pop(srb_sampler* s, int32_t* out);
+int srb_sampler_ring_stop(srb_sampler* s);
 
 /* ---------------------------------------------------------------------------------------
  * Row-sharded multi-GPU propagation.  Rank r owns the contiguous row block

@@ -22,11 +22,13 @@ class SrbError(RuntimeError):
 
 
 class HubSplit(C.Structure):
-    _fields_ = [("n_rows", C.c_int32), ("n_work", C.c_int32), ("first", VP), ("work", VP), ("part", VP)]
+    _fields_ = [("n_rows", C.c_int32), ("n_work", C.c_int32), ("first", VP), ("work", VP), ("part", VP), ("seg", VP), ("seg_cnt", VP),
+                ("order_cta", VP), ("order_warp", VP), ("n_cta", C.c_int32), ("n_warp", C.c_int32)]
 
 
 HUB_CHUNK = 2048    # SRB_HUB_CHUNK
 HUB_MIN_NNZ = 4096  # SRB_HUB_MIN_NNZ
+HUB_WARP_SEG = 256  # SRB_HUB_WARP_SEG
 
 
 class SpmmDesc(C.Structure):
@@ -189,6 +191,9 @@ SYMBOLS = {
     "srb_sampler_next_batch_negs": (C.c_int, [VP, C.c_int32, C.c_int32, c_i32p, c_i32p, c_i32p]),
     "srb_sampler_epoch": (C.c_int64, [VP, C.c_int32, C.c_int32, c_i32p, C.c_int64]),
     "srb_sampler_pairs": (C.c_int64, [VP]),
+    "srb_sampler_ring_start": (C.c_int, [VP, C.c_int32, C.c_int32, C.c_int32]),
+    "srb_sampler_ring_pop": (C.c_int, [VP, c_i32p]),
+    "srb_sampler_ring_stop": (C.c_int, [VP]),
     "srb_spmm_csr_allgather": (C.c_int, [C.POINTER(SpmmShardedDesc), VP]),
     "srb_shard_plan": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(ShardLayout)]),
     "srb_shard_step": (C.c_int, [C.POINTER(ShardDesc), VP]),

@@ -14,7 +14,10 @@
 #include <stdint.h>
 #include <string.h>
 #include <algorithm>
+#include <condition_variable>
+#include <mutex>
 #include <new>
+#include <thread>
 #include <vector>
 #include "selfrec_b200.h"
 
@@ -32,6 +35,36 @@ struct srb_sampler {
   int64_t ptr;
   bool epoch_open;
   std::vector<uint64_t> ubits, ibits;  // scratch bitmaps of sorted_unique
+
+  // sample-ahead ring (srb_sampler_ring_*): one native producer thread fills `ring_depth` batch buffers ahead of the
+  // consumer.  The producer is the only reader of the MT19937 state while it runs, so the stream of draws -- hence
+  // every batch -- is what the sequential calls would produce.
+  std::thread ring_thread;
+  std::mutex ring_mu;
+  std::condition_variable ring_cv;
+  std::vector<int32_t> ring_buf;   // [depth][words]
+  std::vector<int32_t> ring_b;     // batch size of each slot (0 = end of epoch, < 0 = error code)
+  int64_t ring_words = 0;
+  int ring_depth = 0;
+  int64_t ring_head = 0, ring_tail = 0;  // produced / consumed counts
+  bool ring_stop = false, ring_running = false;
+  int32_t ring_bs = 0, ring_cap = 0;
+  // generator state after each produced batch (625 words + ptr), and after the last CONSUMED one: a ring that is
+  // stopped early puts the sampler back there, so the caller sees the stream exactly where it stopped reading
+  struct Snap {
+    uint32_t mt[624];
+    int mti;
+    int64_t ptr;
+    bool open;
+  };
+  std::vector<Snap> ring_snap;
+  Snap ring_consumed;
+  void snap(Snap& d) const {
+    memcpy(d.mt, mt, sizeof mt);
+    d.mti = mti;
+    d.ptr = ptr;
+    d.open = epoch_open;
+  }
 
   inline uint32_t genrand() {
     static const uint32_t mag01[2] = {0x0u, 0x9908b0dfu};
@@ -123,7 +156,12 @@ extern "C" srb_sampler* srb_sampler_create(const int32_t* users, const int32_t* 
   return s;
 }
 
-extern "C" void srb_sampler_destroy(srb_sampler* s) { delete s; }
+extern "C" int srb_sampler_ring_stop(srb_sampler* s);
+
+extern "C" void srb_sampler_destroy(srb_sampler* s) {
+  if (s) srb_sampler_ring_stop(s);
+  delete s;
+}
 
 extern "C" int srb_sampler_set_state(srb_sampler* s, const uint32_t* mt625) {
   if (!s || !mt625) {
@@ -283,6 +321,98 @@ extern "C" int srb_sampler_next_batch_negs(srb_sampler* s, int32_t batch_size, i
   }
   s->ptr = end;
   return b;
+}
+
+// ---- sample-ahead ring ---------------------------------------------------------------------------------------------
+// The host sampler costs ~0.2 ms per batch on one core; a training step that is faster than that would wait for
+// it.  One native thread samples ahead (no GIL, no per-batch Python hand-off), the consumer pops finished batches.
+static void ring_producer(srb_sampler* s) {
+  while (true) {
+    int slot;
+    {
+      std::unique_lock<std::mutex> lk(s->ring_mu);
+      s->ring_cv.wait(lk, [&] { return s->ring_stop || s->ring_head - s->ring_tail < s->ring_depth; });
+      if (s->ring_stop) return;
+      slot = (int)(s->ring_head % s->ring_depth);
+    }
+    const int b = srb_sampler_next_batch(s, s->ring_bs, s->ring_cap, s->ring_buf.data() + (size_t)slot * s->ring_words);
+    s->snap(s->ring_snap[slot]);
+    {
+      std::lock_guard<std::mutex> lk(s->ring_mu);
+      s->ring_b[slot] = b;
+      ++s->ring_head;
+    }
+    s->ring_cv.notify_all();
+    if (b <= 0) return;  // end of the epoch (or an error): the state is final
+  }
+}
+
+extern "C" int srb_sampler_ring_start(srb_sampler* s, int32_t batch_size, int32_t batch_cap, int32_t depth) {
+  if (!s || batch_size <= 0 || batch_cap < batch_size || depth < 1 || depth > 1024) {
+    srb::set_error("sampler_ring_start: bad arguments");
+    return SRB_ERR_ARG;
+  }
+  if (s->ring_running) {
+    srb::set_error("sampler_ring_start: a ring is already running");
+    return SRB_ERR_STATE;
+  }
+  if (!s->epoch_open) {
+    srb::set_error("sampler_ring_start: begin_epoch was not called");
+    return SRB_ERR_STATE;
+  }
+  s->ring_words = srb_batch_words(batch_cap);
+  s->ring_depth = depth;
+  s->ring_bs = batch_size;
+  s->ring_cap = batch_cap;
+  s->ring_buf.assign((size_t)depth * s->ring_words, 0);
+  s->ring_b.assign(depth, 0);
+  s->ring_snap.resize(depth);
+  s->snap(s->ring_consumed);
+  s->ring_head = s->ring_tail = 0;
+  s->ring_stop = false;
+  s->ring_running = true;
+  s->ring_thread = std::thread(ring_producer, s);
+  return SRB_OK;
+}
+
+extern "C" int srb_sampler_ring_pop(srb_sampler* s, int32_t* out) {
+  if (!s || !out || !s->ring_running) {
+    srb::set_error("sampler_ring_pop: no ring is running");
+    return SRB_ERR_STATE;
+  }
+  int slot, b;
+  {
+    std::unique_lock<std::mutex> lk(s->ring_mu);
+    s->ring_cv.wait(lk, [&] { return s->ring_head > s->ring_tail; });
+    slot = (int)(s->ring_tail % s->ring_depth);
+    b = s->ring_b[slot];
+  }
+  if (b > 0) memcpy(out, s->ring_buf.data() + (size_t)slot * s->ring_words, (size_t)s->ring_words * sizeof(int32_t));
+  {
+    std::lock_guard<std::mutex> lk(s->ring_mu);
+    s->ring_consumed = s->ring_snap[slot];
+    if (b > 0) ++s->ring_tail;  // the end marker stays: every later pop returns it again
+  }
+  s->ring_cv.notify_all();
+  return b;
+}
+
+extern "C" int srb_sampler_ring_stop(srb_sampler* s) {
+  if (!s) return SRB_ERR_ARG;
+  if (!s->ring_running) return SRB_OK;
+  {
+    std::lock_guard<std::mutex> lk(s->ring_mu);
+    s->ring_stop = true;
+  }
+  s->ring_cv.notify_all();
+  if (s->ring_thread.joinable()) s->ring_thread.join();
+  s->ring_running = false;
+  // batches sampled ahead but never read are un-drawn: back to the state after the last batch the caller consumed
+  memcpy(s->mt, s->ring_consumed.mt, sizeof s->mt);
+  s->mti = s->ring_consumed.mti;
+  s->ptr = s->ring_consumed.ptr;
+  s->epoch_open = s->ring_consumed.open;
+  return SRB_OK;
 }
 
 extern "C" int64_t srb_sampler_epoch(srb_sampler* s, int32_t batch_size, int32_t batch_cap, int32_t* out, int64_t out_words) {

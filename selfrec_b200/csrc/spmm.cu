@@ -246,15 +246,22 @@ __global__ void __launch_bounds__(256) spmm_hub_kernel(const SpmmArgs a) {
   const int wib = threadIdx.x >> 5;
   const int grp = lane / LPR;
   const int gl = lane % LPR;
-  const int n_work = a.n_vlong_dev ? min(a.n_vlong_dev[4], a.n_work) : a.n_work;
+  const int n_work = a.seg ? a.n_cta : (a.n_vlong_dev ? min(a.n_vlong_dev[4], a.n_work) : a.n_work);
   __shared__ float4 part[8][2][LPR];
-  for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-    const int row = __ldg(a.hub_work + 2 * w);
-    const int ci = __ldg(a.hub_work + 2 * w + 1);
-    const int rbeg = __ldg(a.rowptr + row), rend = __ldg(a.rowptr + row + 1);
-    const int beg = min(rend, rbeg + ci * SRB_HUB_CHUNK);
-    const int end = min(rend, beg + SRB_HUB_CHUNK);
-    constexpr int per = SRB_HUB_CHUNK / 8;  // non-zeros per warp, a multiple of 32
+  for (int k = blockIdx.x; k < n_work; k += gridDim.x) {
+    int w = k, beg, end;
+    if (a.seg) {  // column-blocked segments, in (column block, row) order
+      w = __ldg(a.order_cta + k);
+      beg = __ldg(a.seg + 2 * w);
+      end = __ldg(a.seg + 2 * w + 1);
+    } else {
+      const int row = __ldg(a.hub_work + 2 * w);
+      const int ci = __ldg(a.hub_work + 2 * w + 1);
+      const int rbeg = __ldg(a.rowptr + row), rend = __ldg(a.rowptr + row + 1);
+      beg = min(rend, rbeg + ci * SRB_HUB_CHUNK);
+      end = min(rend, beg + SRB_HUB_CHUNK);
+    }
+    constexpr int per = SRB_HUB_CHUNK / 8;  // non-zeros per warp, a multiple of 32 (segments are at most a chunk long)
     const int wbeg = beg + wib * per;
     const int wend = min(end, wbeg + per);
     float4 acc0 = f4_zero(), acc1 = f4_zero();
@@ -281,6 +288,29 @@ __global__ void __launch_bounds__(256) spmm_hub_kernel(const SpmmArgs a) {
   }
 }
 
+// Short segments of the column-blocked lists: a warp each (lane groups stride the segment, like a "long" row).
+template <int D, bool MASKED>
+__global__ void __launch_bounds__(256) spmm_seg_warp_kernel(const SpmmArgs a) {
+  constexpr int LPR = D / 8;
+  const int lane = threadIdx.x & 31;
+  const int grp = lane / LPR;
+  const int gl = lane % LPR;
+  const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int k = warp0; k < a.n_warp; k += nwarps) {
+    const int w = __ldg(a.order_warp + k);
+    const int beg = __ldg(a.seg + 2 * w), end = __ldg(a.seg + 2 * w + 1);
+    float4 acc0 = f4_zero(), acc1 = f4_zero();
+    spmm_gather<D, MASKED>(a, beg + grp * LPR, end, 32, gl, acc0, acc1);
+    xor_reduce_groups(acc0, acc1, LPR);
+    if (grp == 0) {
+      float* dst = a.hub_part + (size_t)w * D + gl * 4;
+      st4(dst, acc0);
+      st4(dst + D / 2, acc1);
+    }
+  }
+}
+
 // Split rows, second half: add up the chunk sums of spmm_hub_kernel (chunk order), then the common epilogue.
 // One warp per row; its own launch so that the main kernel's register budget stays what it was.
 template <int D>
@@ -297,7 +327,7 @@ __global__ void __launch_bounds__(256) spmm_hub_finish_kernel(const SpmmArgs a) 
     const int row = __ldg(a.row_order + vr);
     const int first = __ldg(a.hub_first + vr);
     const int deg = __ldg(a.rowptr + row + 1) - __ldg(a.rowptr + row);
-    const int nch = (deg + SRB_HUB_CHUNK - 1) / SRB_HUB_CHUNK;
+    const int nch = a.seg ? __ldg(a.seg_cnt + vr) : (deg + SRB_HUB_CHUNK - 1) / SRB_HUB_CHUNK;
     float4 acc0 = f4_zero(), acc1 = f4_zero();
     for (int c = grp; c < nch; c += RPW) {
       const float* src = a.hub_part + (size_t)(first + c) * D + gl * 4;
@@ -451,6 +481,12 @@ template <int D>
 static void launch_spmm_d(const SpmmArgs& a, int hub_blocks, int blocks, cudaStream_t st) {
   const bool m = a.col_mask != nullptr;
   if (hub_blocks > 0) {
+    if (a.seg && a.n_warp > 0) {
+      const int wb = max(1, min((a.n_warp + 7) / 8, blocks));
+      if (m) spmm_seg_warp_kernel<D, true><<<wb, 256, 0, st>>>(a);
+      else spmm_seg_warp_kernel<D, false><<<wb, 256, 0, st>>>(a);
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
     if (m) spmm_hub_kernel<D, true><<<hub_blocks, 256, 0, st>>>(a);
     else spmm_hub_kernel<D, false><<<hub_blocks, 256, 0, st>>>(a);
     const int nh = a.n_vlong_dev ? a.n_rows : a.n_huge;  // (device-counted lists: the capacity)
@@ -472,7 +508,7 @@ int launch_spmm(const SpmmArgs& a, int d, cudaStream_t st) {
   const long long cap = (long long)sm_count() * 8;  // 8 x 256 threads = full residency
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  long long hub_blocks = a.n_work;  // (device-counted lists: the capacity)
+  long long hub_blocks = a.seg ? (a.n_cta > 0 ? a.n_cta : (a.n_work > 0 ? 1 : 0)) : a.n_work;  // (device-counted lists: the capacity)
   if (hub_blocks > cap) hub_blocks = cap;
   switch (d) {
     case 32: launch_spmm_d<32>(a, (int)hub_blocks, (int)blocks, st); break;
@@ -499,13 +535,22 @@ int fill_args(const srb_spmm_desc* d, SpmmArgs& a) {
   a.n_vlong_dev = d->row_order ? d->n_vlong_dev : nullptr;
   // split rows: static lists take the counts from the desc, device-classified lists from n_vlong_dev[0] / [4]
   const bool hub = d->row_order && d->hub.n_work > 0 && (a.n_vlong_dev || d->hub.n_rows > 0);
-  SRB_REQUIRE(!hub || (d->hub.first && d->hub.work && d->hub.part), "spmm: split-row lists incomplete");
+  SRB_REQUIRE(!hub || (d->hub.first && (d->hub.work || d->hub.seg) && d->hub.part), "spmm: split-row lists incomplete");
   SRB_REQUIRE(!hub || d->hub.n_rows <= d->n_rows, "spmm: more split rows than rows");
   a.n_huge = (hub && !a.n_vlong_dev) ? d->hub.n_rows : 0;
   a.hub_first = hub ? d->hub.first : nullptr;
   a.hub_work = hub ? d->hub.work : nullptr;
   a.hub_part = hub ? d->hub.part : nullptr;
   a.n_work = hub ? d->hub.n_work : 0;
+  const bool segs = hub && !a.n_vlong_dev && d->hub.seg != nullptr;
+  SRB_REQUIRE(!segs || (d->hub.seg_cnt && (d->hub.n_cta == 0 || d->hub.order_cta) && (d->hub.n_warp == 0 || d->hub.order_warp)),
+              "spmm: column-blocked split-row lists incomplete");
+  a.seg = segs ? d->hub.seg : nullptr;
+  a.seg_cnt = segs ? d->hub.seg_cnt : nullptr;
+  a.order_cta = segs ? d->hub.order_cta : nullptr;
+  a.order_warp = segs ? d->hub.order_warp : nullptr;
+  a.n_cta = segs ? d->hub.n_cta : 0;
+  a.n_warp = segs ? d->hub.n_warp : 0;
   const int rest = d->n_rows - a.n_huge;
   a.n_vlong = (d->row_order && d->n_vlong_rows > 0) ? (d->n_vlong_rows < rest ? d->n_vlong_rows : rest) : 0;
   a.col_mask = d->col_mask;

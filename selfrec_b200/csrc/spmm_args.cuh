@@ -19,6 +19,13 @@ struct SpmmArgs {
   const int32_t* hub_work;   // [n_work][2] (row, chunk index)
   int32_t n_work;
   float* hub_part;           // [n_work, D] partial sums of the chunks
+  // column-blocked static lists (srb_hub_split.seg): segment w = CSR positions [seg[2w], seg[2w+1])
+  const int32_t* seg;
+  const int32_t* seg_cnt;
+  const int32_t* order_cta;
+  const int32_t* order_warp;
+  int32_t n_cta;
+  int32_t n_warp;
   const float* X;
   float* Y;
   const float* extra;

@@ -5,6 +5,7 @@ computation is a hand-written sm_100a kernel reached through ctypes with raw poi
 All ops are stream-ordered on torch's current stream and raise SrbError without a GPU.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -67,6 +68,49 @@ def classify_rows(rowptr):
         out.update(hub_first=first.to(torch.int32).contiguous(), hub_work=torch.stack([wrow, wci], 1).to(torch.int32).contiguous(),
                    n_work=n_work)
     return out
+
+
+HUB_BLOCK_BYTES = 32 << 20  # X rows of one column block of the column-blocked split-row lists
+
+
+def column_blocked_segments(rowptr, colidx, rows, n_cols, d):
+    """Column-blocked work lists of the split rows `rows` (device tensors; srb_hub_split.seg in the header): every
+    split row is cut at column-block boundaries (block = HUB_BLOCK_BYTES of X rows) and at most HUB_CHUNK non-zeros,
+    and the segments are ordered by (column block, row) so that one block of X stays L2-resident while ALL rows'
+    segments of that block are processed.  Returns dict(seg, first, cnt, order_cta, order_warp) or None when the
+    matrix has a single column block."""
+    W = max(4096, HUB_BLOCK_BYTES // (4 * d))
+    if n_cols <= 2 * W or rows.numel() == 0:
+        return None
+    dev = rowptr.device
+    rp = rowptr.to(torch.int64)
+    beg, end = rp[rows], rp[rows + 1]
+    deg = end - beg
+    n_rows = rows.numel()
+    total = int(deg.sum())
+    slot = torch.repeat_interleave(torch.arange(n_rows, device=dev), deg, output_size=total)      # split-row index of every non-zero
+    pos = torch.arange(total, device=dev) - torch.repeat_interleave(torch.cumsum(deg, 0) - deg, deg, output_size=total) + beg[slot]
+    blk = colidx[pos].to(torch.int64) // W
+    nblk = (n_cols + W - 1) // W
+    key = slot * nblk + blk                                          # non-decreasing: rows ascending, columns ascending within a row
+    ukey, cnt = torch.unique_consecutive(key, return_counts=True)
+    sbeg = pos[torch.cumsum(cnt, 0) - cnt]                           # CSR position of each (row, block) segment
+    # cut segments longer than a chunk
+    pieces = (cnt + _lib.HUB_CHUNK - 1) // _lib.HUB_CHUNK
+    n_seg = int(pieces.sum())
+    src = torch.repeat_interleave(torch.arange(ukey.numel(), device=dev), pieces, output_size=n_seg)
+    sub = torch.arange(n_seg, device=dev) - torch.repeat_interleave(torch.cumsum(pieces, 0) - pieces, pieces, output_size=n_seg)
+    b = sbeg[src] + sub * _lib.HUB_CHUNK
+    e = torch.minimum(b + _lib.HUB_CHUNK, sbeg[src] + cnt[src])
+    srow = ukey[src] // nblk
+    sblk = ukey[src] % nblk
+    per_row = torch.bincount(srow, minlength=n_rows)
+    first = torch.cumsum(per_row, 0) - per_row                       # slots are row-major: a row's segments are consecutive
+    order = torch.sort(sblk * n_rows + srow, stable=True).indices    # processing order: column block, then row
+    long_seg = (e - b)[order] > _lib.HUB_WARP_SEG
+    i32 = lambda t: t.to(torch.int32).contiguous()
+    return dict(seg=i32(torch.stack([b, e], 1)), first=i32(first), cnt=i32(per_row), order_cta=i32(order[long_seg]),
+                order_warp=i32(order[~long_seg]), n_seg=n_seg, block_cols=W)
 
 
 class SparseAdj:
@@ -182,14 +226,27 @@ class SparseAdj:
         return NotImplemented
 
     def hub_struct(self, d):
-        """srb_hub_split of this graph for embedding size d (the partial-sum scratch is allocated on first use)."""
+        """srb_hub_split of this graph for embedding size d (lists and partial-sum scratch are made on first use).
+        Matrices wider than two column blocks get the column-blocked lists (see column_blocked_segments)."""
         h = _lib.HubSplit()
         if self.n_huge:
-            part = self._hub_part.get(d)
-            if part is None:
-                part = self._hub_part[d] = torch.empty((self.n_work, d), device=self.device, dtype=torch.float32)
-            h.n_rows, h.n_work = self.n_huge, self.n_work
-            h.first, h.work, h.part = _p(self.hub_first), _p(self.hub_work), _p(part)
+            ent = self._hub_part.get(d)
+            if ent is None:
+                segs = None
+                if os.environ.get("SRB_HUB_COLBLOCK", "1") != "0":
+                    segs = column_blocked_segments(self.rowptr, self.colidx, self.row_order[: self.n_huge].to(torch.int64), self.shape[1], d)
+                n_part = segs["n_seg"] if segs else self.n_work
+                ent = self._hub_part[d] = (torch.empty((n_part, d), device=self.device, dtype=torch.float32), segs)
+            part, segs = ent
+            h.n_rows, h.part = self.n_huge, _p(part)
+            if segs:
+                h.n_work, h.first = segs["n_seg"], _p(segs["first"])
+                h.seg, h.seg_cnt = _p(segs["seg"]), _p(segs["cnt"])
+                h.order_cta, h.order_warp = _p(segs["order_cta"]), _p(segs["order_warp"])
+                h.n_cta, h.n_warp = int(segs["order_cta"].numel()), int(segs["order_warp"].numel())
+                h.work = _p(self.hub_work)
+            else:
+                h.n_work, h.first, h.work = self.n_work, _p(self.hub_first), _p(self.hub_work)
         return h
 
     def graph_struct(self, d):

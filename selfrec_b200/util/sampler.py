@@ -63,6 +63,18 @@ class NativePairSampler:
             _lib.check(b, "srb_sampler_next_batch")
         return b
 
+    def ring_start(self, batch_size, batch_cap, depth=16):
+        _lib.check(self._lib.srb_sampler_ring_start(self.handle, batch_size, batch_cap, depth), "srb_sampler_ring_start")
+
+    def ring_pop(self, out):
+        b = self._lib.srb_sampler_ring_pop(self.handle, out.ctypes.data_as(_lib.c_i32p))
+        if b < 0:
+            _lib.check(b, "srb_sampler_ring_pop")
+        return b
+
+    def ring_stop(self):
+        _lib.check(self._lib.srb_sampler_ring_stop(self.handle), "srb_sampler_ring_stop")
+
     def epoch(self, batch_size, batch_cap):
         """All batches of one epoch (after begin_epoch): int32 array [n_batches, words]."""
         words = _lib.BATCH_HEADER + 5 * batch_cap
@@ -74,22 +86,40 @@ class NativePairSampler:
         return out[:got]
 
 
-def stream_epoch(sampler, data, batch_size, batch_cap):
-    """One epoch of batch buffers (srb_sampler_next_batch layout), sampled one native call per batch into ONE
-    reused int32 buffer (the consumer copies it, e.g. into a pinned slot): sampling batch t+1 overlaps the GPU step
-    of batch t, and 41 KB stay cache-resident instead of a 25 MB epoch array being first-touched (0.2 vs 0.4 ms
-    per batch at yelp2018).  (A producer thread sampling ahead was tried and dropped: the queue hand-offs under the
-    GIL cost more than the 0.2 ms they hide.)  Python's `random` state is taken at the start and handed back when
-    the epoch ends or the generator is closed; data.training_data gets the epoch's shuffle."""
+def stream_epoch(sampler, data, batch_size, batch_cap, ring_depth=16):
+    """One epoch of batch buffers (srb_sampler_next_batch layout) in ONE reused int32 buffer (the consumer copies
+    it, e.g. into a pinned slot).  The batches come from the native sample-ahead ring: a C++ thread samples up to
+    `ring_depth` batches ahead (0.2 ms each on one core) while Python enqueues GPU work, so the sampler stops being
+    the ceiling of a step that is faster than that (a Python producer thread was tried in round 1 and dropped: its
+    queue hand-offs under the GIL cost more than they hid).  ring_depth=0: one native call per batch.  Python's
+    `random` state is taken at the start and handed back when the epoch ends or the generator is closed (batches the
+    ring sampled ahead but nobody read are un-drawn: the state is the reference's at that point of the stream);
+    data.training_data gets the epoch's shuffle."""
+    # an epoch generator that was abandoned without close() (e.g. zip(range(n), gen)) still owns the ring and a
+    # pending state hand-back: retire it now -- its own `finally`, whenever the garbage collector gets to it, must
+    # neither stop the new ring nor overwrite Python's `random` state with a stale one
+    if getattr(sampler, "_open_epoch", None) is not None:
+        sampler.ring_stop()
+        sampler.push_state()
+    token = object()
+    sampler._open_epoch = token
     sampler.pull_state()
     try:
         perm = sampler.begin_epoch(want_perm=True)
         permute_training_data(data, perm)
         buf = np.empty(_lib.BATCH_HEADER + 5 * batch_cap, dtype=np.int32)
-        while sampler.next_batch(batch_size, batch_cap, buf) > 0:
-            yield buf
+        if ring_depth > 0:
+            sampler.ring_start(batch_size, batch_cap, ring_depth)
+            while sampler._open_epoch is token and sampler.ring_pop(buf) > 0:
+                yield buf
+        else:
+            while sampler._open_epoch is token and sampler.next_batch(batch_size, batch_cap, buf) > 0:
+                yield buf
     finally:
-        sampler.push_state()
+        if sampler._open_epoch is token:
+            sampler._open_epoch = None
+            sampler.ring_stop()
+            sampler.push_state()
 
 
 def _sampler_for(data):

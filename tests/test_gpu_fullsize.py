@@ -147,3 +147,119 @@ def test_epoch_of_native_batches_trains(yelp, in_tmp_cwd):
     assert np.isfinite(eng.params.cpu().numpy()).all()
     assert last[0] < first[0]  # BPR loss goes down from log(2)
     assert abs(first[0] - np.log(2)) < 0.01
+
+
+# ------------------------------------------------------------------------------------------
+# the other configs of BASELINE.json at full shape: one step against the float64 oracle
+# ------------------------------------------------------------------------------------------
+def _words(u, i, j, cap):
+    w = np.zeros(4 + 5 * cap, dtype=np.int32)
+    uq, iq = np.unique(u), np.unique(i)
+    w[0], w[1], w[2] = len(u), len(uq), len(iq)
+    for s, arr in enumerate((u, i, j, uq, iq)):
+        w[4 + s * cap:4 + s * cap + len(arr)] = arr
+    return w
+
+
+def _negatives(data, u, rng):
+    rp, ri = data.rated_csr()
+    return np.array([next(x for x in rng.integers(0, data.item_num, 64) if x not in ri[rp[uu]:rp[uu + 1]]) for uu in u], dtype=np.int32)
+
+
+def _check_step(eng, out, E0, orc, lr=1e-3):
+    """losses to 1e-4; Adam's first moment m = 0.1 g is linear in the gradient, so it is the well-conditioned check
+    of the whole backward; parameters where the gradient is not within rounding of zero."""
+    import torch
+    torch.cuda.synchronize()
+    los = eng.losses.cpu().numpy()
+    for got, want in ((los[0], out["rec"]), (los[1], out["l2"]), (los[2], out["cl"])):
+        assert abs(got - want) <= 1e-4 * abs(want) + 1e-12, (got, want)
+    g = out["grad"]
+    m = eng.m.cpu().numpy()
+    assert np.abs(m - 0.1 * g).max() <= 1e-4 * np.abs(0.1 * g).max()
+    big = np.abs(g) > 1e-3 * np.abs(g).max()
+    P, _, _ = orc.adam_step(E0, g.astype(np.float32), np.zeros_like(E0), np.zeros_like(E0), 1, lr)
+    np.testing.assert_allclose(eng.params.cpu().numpy()[big], P[big], rtol=1e-4, atol=2e-6)
+
+
+def test_lightgcn_step_yelp_shape_vs_oracle(yelp, orc, in_tmp_cwd):
+    """configs[1]: LightGCN, yelp2018 shape, 3 layers, d=64, B=2048 (LightGCN.py:21-29)."""
+    import torch
+    from selfrec_b200.engine import TrainEngine
+    torch.manual_seed(1)
+    eng = TrainEngine("LightGCN", yelp, 64, 3, 2048, 1e-3, 1e-4, l2_div=2048.0)
+    E0 = eng.params.cpu().numpy().copy()
+    rng = np.random.default_rng(3)
+    u, i = yelp.pair_users[5000:7048].copy(), yelp.pair_items[5000:7048].copy()
+    j = _negatives(yelp, u, rng)
+    eng.step(_words(u, i, j, 2048))
+    out = orc.train_step("LightGCN", yelp.norm_adj.tocsr(), E0, eng.U, u, i, j, n_layers=3, reg=1e-4, batch_size=2048)
+    _check_step(eng, out, E0, orc)
+
+
+def test_sgl_step_kindle_shape_device_views_vs_oracle(orc, built_lib, in_tmp_cwd):
+    """configs[3]: SGL edge-drop at amazon-kindle shape (138 333 x 98 572 x 1 525 091 + 2 822 duplicate lines -> 2.0
+    entries, dropped graphs reset them to 1): the two view graphs are drawn like the reference draws them and BUILT ON
+    THE DEVICE; the step (three encoders on three graphs, one InfoNCE over cat(users, items), SGL.py:30-41,98-125)
+    must match the oracle run on the scipy-route view graphs."""
+    import random
+    import scipy.sparse as sp
+    import torch
+    from selfrec_b200 import synth
+    from selfrec_b200.data.augmentor import GraphAugmentor, sample_range
+    from selfrec_b200.data.device_graph import DeviceBipartite
+    from selfrec_b200.engine import TrainEngine
+    U, I, nnz = synth.SHAPES["amazon-kindle"]
+    pu, pi = synth.make_pairs(U, I, nnz, seed=4)
+    dup = np.random.default_rng(4).choice(nnz, 2822, replace=False)
+    data = synth.ArrayInteraction(np.concatenate([pu, pu[dup]]), np.concatenate([pi, pi[dup]]), U, I)
+    assert data.interaction_mat.nnz == nnz and data.interaction_mat.data.max() == 2.0
+    bip = DeviceBipartite.from_interaction_mat(data.interaction_mat, "cuda")
+    random.seed(21)
+    host_views = [data.convert_to_laplacian_mat(GraphAugmentor.edge_dropout(data.interaction_mat, 0.1)) for _ in range(2)]
+    random.seed(21)
+    dev_views = [bip.assemble(keep_idx=sample_range(bip.nnz, int(bip.nnz * 0.9)), reset_weights=True) for _ in range(2)]
+    for a, h in zip(dev_views, host_views):  # bit-identical graphs
+        h = sp.csr_matrix(h)
+        h.sort_indices()
+        assert np.array_equal(a.rowptr.cpu().numpy(), h.indptr) and np.array_equal(a.colidx.cpu().numpy(), h.indices)
+        assert np.array_equal(a.vals.cpu().numpy().view(np.uint32), h.data.astype(np.float32).view(np.uint32))
+    torch.manual_seed(2)
+    eng = TrainEngine("SGL", data, 64, 3, 2048, 1e-3, 1e-4, tau=0.2, cl_rate=0.1)
+    eng.set_view_graphs(*dev_views)
+    E0 = eng.params.cpu().numpy().copy()
+    rng = np.random.default_rng(5)
+    sel = rng.choice(len(pu), 2048, replace=False)
+    u, i = pu[sel].copy(), pi[sel].copy()
+    j = _negatives(data, u, rng)
+    eng.step(_words(u, i, j, 2048))
+    out = orc.train_step("SGL", data.norm_adj.tocsr(), E0, eng.U, u, i, j, n_layers=3, reg=1e-4, batch_size=2048, tau=0.2, cl_rate=0.1,
+                         view_csr=[sp.csr_matrix(h) for h in host_views])
+    _check_step(eng, out, E0, orc)
+
+
+def test_simgcl_step_one_million_nodes_vs_oracle(orc, built_lib, in_tmp_cwd):
+    """configs[4] recipe (Zipf 1.1, generated + normalised on the GPU, split rows) on a graph of 1.0 M nodes
+    (800 k x 200 k x 16 M), SimGCL: three encoders, merged Horner chain (SimGCL.py:25-36,81-93), noise as an input."""
+    import scipy.sparse as sp
+    import torch
+    from selfrec_b200 import synth
+    from selfrec_b200.engine import TrainEngine
+    data = synth.make_device_interaction((800_000, 200_000, 16_000_000), seed=3, alpha=1.1)
+    adj = data.norm_adj
+    assert adj.shape[0] == 1_000_000 and adj.n_huge > 0
+    d, L, B = 64, 2, 2048
+    torch.manual_seed(4)
+    eng = TrainEngine("SimGCL", data, d, L, B, 1e-3, 1e-4, eps=0.1, tau=0.2, cl_rate=0.5)
+    rng = np.random.default_rng(6)
+    noise = rng.random((2, L, eng.N, d), dtype=np.float32)
+    eng.set_noise_tensor(torch.from_numpy(noise).cuda())
+    E0 = eng.params.cpu().numpy().copy()
+    pu, pi = data.pair_users, data.pair_items
+    sel = rng.choice(len(pu), B, replace=False)
+    u, i = pu[sel].copy(), pi[sel].copy()
+    j = _negatives(data, u, rng)
+    eng.step(_words(u, i, j, B))
+    A = sp.csr_matrix((adj.vals.cpu().numpy(), adj.colidx.cpu().numpy(), adj.rowptr.cpu().numpy()), shape=adj.shape)
+    out = orc.train_step("SimGCL", A, E0, eng.U, u, i, j, n_layers=L, reg=1e-4, batch_size=B, eps=0.1, tau=0.2, cl_rate=0.5, noise=noise)
+    _check_step(eng, out, E0, orc)

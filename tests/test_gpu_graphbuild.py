@@ -187,3 +187,33 @@ def test_sgl_model_views_device_route_equals_reference_route(torch_cuda, tiny_co
         _same_csr(a, r)
     m._epoch_prologue(0)  # and the engine accepts the device handles
     assert m.engine.view_adj[0].rowptr.is_cuda
+
+
+@pytest.mark.parametrize("d", [64, 128])
+def test_spmm_column_blocked_split_rows_vs_oracle(torch_cuda, orc, d, monkeypatch):
+    """Column-blocked split-row lists (srb_hub_split.seg): segments cut at column-block boundaries, processed in
+    (block, row) order by a CTA or a warp each, summed per row in segment order."""
+    torch = torch_cuda
+    from selfrec_b200 import _lib, ops
+    monkeypatch.setattr(ops, "HUB_BLOCK_BYTES", 2048 * 4 * d)  # blocks of 4096 columns (the floor): many blocks at test size
+    rng = np.random.default_rng(d + 1)
+    n_rows, n_cols = 400, 60000
+    deg = rng.integers(0, 40, n_rows)
+    deg[[5, 99, 300, 301]] = [_lib.HUB_MIN_NNZ, 25000, 7000, 59000]
+    rows = np.repeat(np.arange(n_rows), deg)
+    cols = np.concatenate([rng.choice(n_cols, k, replace=False) for k in deg])
+    A = sp.csr_matrix((rng.standard_normal(len(rows)).astype(np.float32), (rows, cols)), shape=(n_rows, n_cols))
+    X = rng.standard_normal((n_cols, d)).astype(np.float32)
+    h = ops.SparseAdj(A).cuda()
+    hs = h.hub_struct(d)
+    assert h.n_huge == 4 and hs.seg and hs.n_cta > 0 and hs.n_warp > 0
+    y = torch.sparse.mm(h, torch.from_numpy(X).cuda()).cpu().numpy()
+    ref = orc.spmm(A, X)
+    assert (np.abs(y - ref) <= 4e-6 * np.abs(A).dot(np.abs(X)) + 1e-30).all()
+    mask_rows = rng.random(n_cols) < 0.05
+    Xm = X * mask_rows[:, None]
+    bits = np.packbits(mask_rows, bitorder="little")
+    bits = np.concatenate([bits, np.zeros((-len(bits)) % 4, np.uint8)]).view(np.int32)
+    ym = torch.empty(n_rows, d, device="cuda")
+    ops._spmm_raw(h, torch.from_numpy(Xm).cuda(), ym, col_mask=torch.from_numpy(bits).cuda())
+    assert (np.abs(ym.cpu().numpy() - orc.spmm(A, Xm)) <= 4e-6 * np.abs(A).dot(np.abs(Xm)) + 1e-30).all()
