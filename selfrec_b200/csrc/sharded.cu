@@ -37,13 +37,6 @@ struct BarrierArgs {
   int world, rank;
 };
 
-__device__ __forceinline__ void st_release_sys(int* p, int v) { asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ int ld_acquire_sys(const int* p) {
-  int v;
-  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
 __global__ void shard_barrier_kernel(const BarrierArgs b) {
   __shared__ int e_s;
   if (threadIdx.x == 0) {
@@ -223,6 +216,30 @@ struct Ctx {
   float* lw(int64_t off) const { return (float*)(loc + off); }
 };
 
+// wait / signal folded into the kernels of a layer (PeerSync in spmm_args.cuh)
+static PeerSync peer_sync(const Ctx& c, bool wait, bool signal) {
+  PeerSync p = {};
+  if (c.G <= 1) return p;
+  for (int q = 0; q < c.G; ++q) p.flags[q] = (int*)((char*)c.s->sym[q] + c.sp.flags);
+  p.epoch = (int*)(c.loc + c.lp.ctrl);
+  p.err = p.epoch + 1;
+  p.counter = p.epoch + 2;
+  p.world = c.G;
+  p.rank = c.rank;
+  p.wait = wait;
+  p.signal = signal;
+  return p;
+}
+
+// wait for the peers' latest signal without sending one (e.g. before adding into rows the peers' reductions store)
+__global__ void shard_wait_kernel(const PeerSync s) { peer_wait(s); }
+
+static int wait_peers(const Ctx& c) {
+  if (c.G <= 1) return SRB_OK;
+  shard_wait_kernel<<<1, 32, 0, c.st>>>(peer_sync(c, true, false));
+  return post_launch("shard_wait_kernel");
+}
+
 static int barrier(const Ctx& c) {
   if (c.G <= 1) return SRB_OK;
   BarrierArgs b = {};
@@ -265,7 +282,7 @@ static int base_args(const Ctx& c, const srb_graph_csr& g, int n_rows, const flo
   p.n_vlong_rows = g.n_vlong_rows;
   p.hub = g.hub;
   p.n_rows = n_rows;
-  p.n_cols = 1;
+  p.n_cols = (&g == &c.s->Ru) ? c.I : c.Ug;
   p.d = c.d;
   p.X = X;
   p.col_mask = mask;
@@ -340,6 +357,9 @@ static int layer(const Ctx& c, const float* xu, const float* xi, const Epi& e) {
       for (int q = 0; q <= c.G; ++q) a.stage_bounds[q] = (int32_t)((int64_t)q * c.I / c.G);
       a.stage_rank = c.rank;
       a.stage_cap = c.sp.stage_cap;
+      // wait: the owners have finished reading the staging areas (and every rank the buffers this layer rewrites);
+      // signal: this rank's partial rows are in place
+      a.ps = peer_sync(c, true, true);
     }
     SRB_TRY(launch_spmm(a, c.d, c.st));
   }
@@ -363,7 +383,6 @@ static int layer(const Ctx& c, const float* xu, const float* xi, const Epi& e) {
   }
   if (c.G == 1) return SRB_OK;
   // ---- item half, part 2: owner-side reduction + epilogue + push to every rank ----
-  SRB_TRY(barrier(c));
   {
     SpmmArgs a;
     SRB_TRY(base_args(c, s->Rt, c.I, xu, nullptr, a));
@@ -374,9 +393,10 @@ static int layer(const Ctx& c, const float* xu, const float* xi, const Epi& e) {
     r.stage_cap = c.sp.stage_cap;
     r.slice_begin = c.ib;
     r.n_slice = c.ib_end - c.ib;
+    a.ps = peer_sync(c, true, true);  // wait: all partials have landed; signal: the finished rows are everywhere
     SRB_TRY(launch_reduce_rows(a, r, c.d, c.st));
   }
-  return barrier(c);
+  return SRB_OK;
 }
 
 // Encoder forward on the sharded tables (R4).  sums: running layer sum / final mean (user local, item owner slice).
@@ -660,6 +680,7 @@ extern "C" int srb_shard_step(const srb_shard_desc* s, void* stream) {
     }
     SRB_TRY(layer(c, au[x], c.mine(c.sp.ai[x]), e));
     x ^= 1;
+    SRB_TRY(wait_peers(c));  // the peers' reductions have stored their slices into this rank's copy: now add to it
     if (c.Ug) SRB_TRY(scatter_segments(au[x], d, merged(fu, lcl == k ? &cu : nullptr), st));
     SRB_TRY(scatter_segments(c.mine(c.sp.ai[x]), d, merged(fi, lcl == k ? &ci : nullptr), st));
   }
@@ -693,5 +714,5 @@ extern "C" int srb_shard_forward(const srb_shard_desc* s, float* out_user, void*
   SRB_REQUIRE(out_user != nullptr || c.Ug == 0, "shard_forward: null output");
   const bool ego = s->model == SRB_MODEL_LIGHTGCN;
   SRB_TRY(encoder(c, ego, 0, 0, 0, out_user, c.mine(c.sp.fin_i), nullptr, -1, true));
-  return SRB_OK;
+  return wait_peers(c);  // every slice of the item output has arrived
 }

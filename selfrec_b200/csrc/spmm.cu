@@ -10,7 +10,10 @@
 
 namespace srb {
 
-__device__ __forceinline__ void st4_cs(float* p, const float4& v) { __stcs(reinterpret_cast<float4*>(p), v); }
+__device__ __forceinline__ void st4_cs(float* p, const float4& v, int stream) {
+  if (stream) __stcs(reinterpret_cast<float4*>(p), v);
+  else st4(p, v);
+}
 
 // store to another rank's copy: a plain P2P store, or one multimem.st that the NVSwitch replicates into every
 // rank's copy of a multicast-mapped buffer
@@ -71,9 +74,9 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmArgs& a, int row, int gl
 #undef SRB_PERT
     }
     if (!valid) return;
-    if (a.Y) {  // written once, read (randomly) by the NEXT product: streaming stores
-      st4_cs(a.Y + off, y0);
-      st4_cs(a.Y + off + HALF, y1);
+    if (a.Y) {  // written once, read (randomly) by the NEXT product
+      st4_cs(a.Y + off, y0, a.stream);
+      st4_cs(a.Y + off + HALF, y1, a.stream);
     }
     if (a.world > 0 && a.peer[0]) {  // fused all-gather: NVLink P2P stores into every rank's layer buffer
 #pragma unroll 1
@@ -90,8 +93,8 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmArgs& a, int row, int gl
       }
       s0 = f4_scale(a.sum_scale, s0);
       s1 = f4_scale(a.sum_scale, s1);
-      st4_cs(a.sum_out + off, s0);
-      st4_cs(a.sum_out + off + HALF, s1);
+      st4_cs(a.sum_out + off, s0, a.stream);
+      st4_cs(a.sum_out + off + HALF, s1, a.stream);
       if (a.world > 0 && a.peer_sum[0]) {
 #pragma unroll 1
         for (int g = 0; g < a.world; ++g) {
@@ -108,8 +111,8 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmArgs& a, int row, int gl
         const size_t o2 = off + h * HALF;
         const float4 g = h ? y1 : y0;
         float4 p4 = *reinterpret_cast<const float4*>(a.ap + o2);
-        float4 m = __ldcs(reinterpret_cast<const float4*>(a.am + o2));
-        float4 v4 = __ldcs(reinterpret_cast<const float4*>(a.av + o2));
+        float4 m = *reinterpret_cast<const float4*>(a.am + o2);
+        float4 v4 = *reinterpret_cast<const float4*>(a.av + o2);
 #define SRB_ADAM1(F)                                          \
   m.F = m.F + a.w1 * (g.F - m.F);                             \
   v4.F = v4.F * a.b2;                                         \
@@ -118,8 +121,8 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmArgs& a, int row, int gl
         SRB_ADAM1(x) SRB_ADAM1(y) SRB_ADAM1(z) SRB_ADAM1(w)
 #undef SRB_ADAM1
         st4(a.ap + o2, p4);
-        st4_cs(a.am + o2, m);
-        st4_cs(a.av + o2, v4);
+        st4_cs(a.am + o2, m, a.stream);
+        st4_cs(a.av + o2, v4, a.stream);
         if (a.world > 0 && a.peer_p[0]) {
 #pragma unroll 1
           for (int g = 0; g < a.world; ++g) st4_peer(a.peer_p[g] + o2, p4, a.peer_mc);
@@ -155,8 +158,10 @@ __device__ __forceinline__ void spmm_gather(const SpmmArgs& a, int p, int end, i
   float v = 0.f;
   bool hit = false;
   if (p + gl < end) {
-    c = __ldcs(a.colidx + p + gl);  // the CSR arrays are read once per product: evict-first, so that they do not push
-    v = __ldcs(a.vals + p + gl);    // gathered X rows out of L2 (at config-5 size the product is bound by those re-reads)
+    // tables beyond L2 (config-5 size: the product is bound by re-reads of gathered X rows): the CSR arrays are read
+    // once per product, so they go evict-first and do not push X rows out; small graphs keep everything L2-resident
+    c = a.stream ? __ldcs(a.colidx + p + gl) : __ldg(a.colidx + p + gl);
+    v = a.stream ? __ldcs(a.vals + p + gl) : __ldg(a.vals + p + gl);
     if (masked) hit = (__ldg(a.col_mask + (c >> 5)) >> (c & 31)) & 1u;
   }
   while (__any_sync(SRB_FULL_MASK, p < end)) {
@@ -164,8 +169,8 @@ __device__ __forceinline__ void spmm_gather(const SpmmArgs& a, int p, int end, i
     float vn = 0.f;
     bool hitn = false;
     if (p + stride + gl < end) {  // prefetch the next iteration's pair
-      cn = __ldcs(a.colidx + p + stride + gl);
-      vn = __ldcs(a.vals + p + stride + gl);
+      cn = a.stream ? __ldcs(a.colidx + p + stride + gl) : __ldg(a.colidx + p + stride + gl);
+      vn = a.stream ? __ldcs(a.vals + p + stride + gl) : __ldg(a.vals + p + stride + gl);
       if (masked) hitn = (__ldg(a.col_mask + (cn >> 5)) >> (cn & 31)) & 1u;
     }
     if (!masked) {
@@ -323,6 +328,7 @@ __global__ void __launch_bounds__(256) spmm_hub_finish_kernel(const SpmmArgs a) 
   const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int n_huge = a.n_vlong_dev ? min(a.n_vlong_dev[0], a.n_rows) : a.n_huge;
+  peer_wait(a.ps);  // (its epilogue may store to peers; the signal is the main kernel's, launched after this one)
   for (int vr = warp0; vr < n_huge; vr += nwarps) {
     const int row = __ldg(a.row_order + vr);
     const int first = __ldg(a.hub_first + vr);
@@ -350,6 +356,7 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmArgs a) {
   const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
 
+  peer_wait(a.ps);
   // (the split rows -- the first n_huge entries of the list -- belong to spmm_hub_kernel / spmm_hub_finish_kernel)
   int n_vlong = a.n_vlong, n_long = a.n_long, n_short = a.n_rows - a.n_huge - a.n_vlong - a.n_long;
   const int32_t* ro_v = a.row_order ? a.row_order + a.n_huge : nullptr;  // the three classes' row lists (null: identity order)
@@ -433,6 +440,7 @@ __global__ void __launch_bounds__(256) reduce_rows_kernel(const SpmmArgs a, cons
   const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int n_items = (r.n_slice + RPW - 1) / RPW;
+  peer_wait(a.ps);  // every rank's partial rows have landed in the staging area
   for (int item = warp0; item < n_items; item += nwarps) {
     const int k = item * RPW + grp;
     const bool valid = k < r.n_slice;
@@ -459,6 +467,7 @@ __global__ void __launch_bounds__(256) reduce_rows_kernel(const SpmmArgs a, cons
     }
     spmm_epilogue<D>(a, r.slice_begin + k, gl, acc0, acc1, valid);
   }
+  peer_signal(a.ps);  // the finished rows are in every rank's copy
 }
 
 int launch_reduce_rows(const SpmmArgs& a, const ReduceArgs& r, int d, cudaStream_t st) {
@@ -580,6 +589,9 @@ int fill_args(const srb_spmm_desc* d, SpmmArgs& a) {
   a.row_begin = 0;
   a.noise_row_base = 0;
   a.peer_mc = 0;
+  a.ps = PeerSync{};
+  // (rows + columns) x d x 4 bytes of dense operands beyond ~3/4 of the 126 MB L2: stream the one-touch data
+  a.stream = ((long long)d->n_rows + d->n_cols) * d->d * 4 > (96ll << 20);
   a.stage_rank = a.stage_cap = 0;
   for (int g = 0; g < 8; ++g) a.peer[g] = a.peer_sum[g] = a.peer_p[g] = a.stage_peer[g] = nullptr;
   for (int g = 0; g < 9; ++g) a.stage_bounds[g] = 0;

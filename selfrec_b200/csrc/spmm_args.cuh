@@ -4,6 +4,60 @@
 
 namespace srb {
 
+// Cross-GPU synchronisation folded into a kernel of the bipartite-sharded step (no separate barrier launch):
+//   wait   -- at kernel start every CTA polls this rank's flag array until all ranks have sent signal number *epoch
+//             (the peers' stores this kernel is about to read, or whose buffers it is about to overwrite, are done);
+//   signal -- at kernel end the last CTA to finish bumps *epoch and stores it into every rank's flag array
+//             (st.release.sys after a system fence: this kernel's peer stores are visible before the flag).
+// Every rank runs the same kernel sequence, so signal numbers agree; a peer that never arrives trips *err after ~30 s.
+struct PeerSync {
+  int* flags[8];  // every rank's flags [8]; flags[rank] is local
+  int* epoch;     // local: signals sent so far
+  int* counter;   // local: CTAs of the signalling kernel that are done
+  int* err;
+  int world, rank;
+  int wait, signal;
+};
+
+__device__ __forceinline__ void st_release_sys(int* p, int v) { asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void peer_wait(const PeerSync& s) {
+  if (!s.wait) return;
+  if ((int)threadIdx.x < s.world) {
+    const int target = *reinterpret_cast<volatile int*>(s.epoch);
+    const int* f = s.flags[s.rank] + threadIdx.x;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(f) < target) {
+      if (clock64() - t0 > 60000000000ll) {  // ~30 s: a peer died; do not hang the GPU
+        *s.err = 1;
+        break;
+      }
+      __nanosleep(32);
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void peer_signal(const PeerSync& s) {
+  if (!s.signal) return;
+  __syncthreads();  // every store of this CTA has been issued
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    if (atomicAdd(s.counter, 1) == (int)gridDim.x - 1) {  // last CTA of the grid
+      *s.counter = 0;
+      __threadfence_system();
+      const int e = *s.epoch + 1;
+      *s.epoch = e;
+      for (int q = 0; q < s.world; ++q) st_release_sys(s.flags[q] + s.rank, e);
+    }
+  }
+}
+
 struct SpmmArgs {
   const int32_t* rowptr;
   const int32_t* colidx;
@@ -49,6 +103,7 @@ struct SpmmArgs {
   float* peer[8];      // layer output -> every rank's buffer
   float* peer_sum[8];  // running sum  -> every rank's buffer
   float* peer_p[8];    // updated parameters (Adam epilogue) -> every rank's copy
+  int32_t stream;          // tables larger than L2: CSR arrays and outputs are touched once per product -> evict-first accesses
   int32_t peer_mc;         // the one peer address is an NVSwitch multicast mapping: stores go out as multimem.st
   int32_t noise_row_base;  // Philox row id = noise_row_base + row_begin + row (global id of a row of a sharded table)
   // partial-sum push (bipartite sharding, item-side product): row r of this rank's partial product goes to the
@@ -57,6 +112,7 @@ struct SpmmArgs {
   int32_t stage_bounds[9];
   int32_t stage_rank;
   int32_t stage_cap;
+  PeerSync ps;
 };
 
 // rows of an item slice summed over the ranks' staged partial products (fixed rank order), then the common epilogue

@@ -79,7 +79,7 @@ class TrainEngine:
             na = data.norm_adj
             self.adj = na if isinstance(na, ops.SparseAdj) else ops.SparseAdj(na)
             self.adj.cuda(dev)
-        ws_bytes = lib.srb_step_workspace_bytes(self.model_id, self.N, self.d, self.B, self.adj.n_work if self.adj is not None else 0)
+        ws_bytes = lib.srb_step_workspace_bytes(self.model_id, self.N, self.d, self.B, self.adj.hub_struct(self.d).n_work if self.adj is not None else 0)
         self.workspace = torch.empty(ws_bytes + 256, device=dev, dtype=torch.uint8)
         ws_ptr = (self.workspace.data_ptr() + 255) // 256 * 256
         self.view_adj = [None, None]
