@@ -423,6 +423,7 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmArgs a) {
     }
     spmm_epilogue<D>(a, row, gl, acc0, acc1, valid);
   }
+  peer_signal(a.ps);  // (sharded item-side product: this rank's partial rows are in the owners' staging areas)
 }
 
 // Owner-side reduction of an item slice (bipartite sharding): every rank's item-side product left its partial rows

@@ -45,7 +45,8 @@ __device__ __forceinline__ void peer_wait(const PeerSync& s) {
 
 __device__ __forceinline__ void peer_signal(const PeerSync& s) {
   if (!s.signal) return;
-  __syncthreads();  // every store of this CTA has been issued
+  __threadfence_system();  // every thread: its peer stores are ordered before what follows
+  __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence_system();
     if (atomicAdd(s.counter, 1) == (int)gridDim.x - 1) {  // last CTA of the grid
