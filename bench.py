@@ -484,7 +484,8 @@ def record_config5(args, dev, world, rank, dist):
     try:
         mid = synth.make_device_interaction(synth.SHAPES["synthetic-2M"], seed=1, alpha=1.1, device=dev)
         mb = device_batches(mid, B, 3, seed=6, dev=dev)
-        rec["parity_2p5M_nodes"] = sharded_vs_single("SimGCL", mid, d, 2, B, mb, steps=2, dev=dev, **kw)
+        rec["parity_2p5M_nodes"] = {"strict_eps0": sharded_vs_single("SimGCL", mid, d, 2, B, mb, steps=2, dev=dev, **dict(kw, eps=0.0)),
+                                    "configured": sharded_vs_single("SimGCL", mid, d, 2, B, mb, steps=2, dev=dev, **kw)}
     except Exception as e:  # noqa: BLE001
         rec["parity_2p5M_nodes"] = {"error": f"{type(e).__name__}: {e}"}
     return rec
@@ -711,14 +712,19 @@ def run_sharded(args, rank, world, local_rank):
     P = pool_host.shape[0]
 
     # ---- self-verification before anything is timed: sharded step == single-GPU engine, on both peer-store routes ----
+    # "strict": eps = 0 -- every compared quantity (losses, Adam moments, clean forward) within 1e-4.
+    # "configured": eps = 0.2 -- sign(y) * noise * eps is discontinuous at y = 0, so an element within fp32 rounding of
+    # zero flips under the sharded summation order; the losses agree to 1e-4, `m_rows_off_frac` says how few rows differ.
     parity = {}
     for route, mc in (("unicast", False), ("multicast", True)):
-        try:
-            r = sharded_vs_single("XSimGCL", data, d, L, B, pool, steps=3, dev=dev, multicast=mc, **xs_kwargs())
-            parity[route if r["route"] == route else f"{route}->({r['route']})"] = r
-        except Exception as e:  # noqa: BLE001
-            parity[route] = {"error": f"{type(e).__name__}: {e}"}
-    parity_max = max([v.get("max_rel", float("inf")) for v in parity.values()])
+        for tag, kw in (("strict_eps0", dict(xs_kwargs(), eps=0.0)), ("configured", xs_kwargs())):
+            try:
+                r = sharded_vs_single("XSimGCL", data, d, L, B, pool, steps=3, dev=dev, multicast=mc, **kw)
+                keep = ("max_rel", "loss_rel", "m_user_rel", "m_item_rel", "final_user_rel", "final_item_rel", "m_rows_off_frac", "route", "steps")
+                parity[f"{route}_{tag}"] = {k: r[k] for k in keep}
+            except Exception as e:  # noqa: BLE001
+                parity[f"{route}_{tag}"] = {"error": f"{type(e).__name__}: {e}"}
+    parity_max = max([v.get("max_rel", float("inf")) for k, v in parity.items() if k.endswith("strict_eps0")])
 
     sh = ShardedEngine("XSimGCL", data, d, L, B, CFG["lr"], CFG["reg"], device=dev, philox_seed=2026, **xs_kwargs())
     l0 = _lib.launch_count()
@@ -818,7 +824,7 @@ def run_sharded(args, rank, world, local_rank):
                    "l2": "no flush: per-step working set > 126 MB L2",
                    "inputs": f"{P} pre-sampled batches resident in HBM on every rank; CUDA-graph replay"},
         "clocks": clk,
-        "parity": parity, "parity_max_rel": parity_max,
+        "parity": parity, "parity_max_rel": parity_max, "parity_note": "parity_max_rel = the strict (eps = 0) runs; see bench.py run_sharded",
         "e2e": {"value": e2e_val, "unit": "steps/s", "h2d_bytes_per_step": int(pool_host.shape[1] * 4), "d2h_bytes_per_step": 16,
                 "note": "every rank: native sampler (same seed) + pinned H2D + sharded step + loss D2H, read one step late"},
         "gpu_launches": int(launches_per_step * args.steps), "launches_per_step": int(launches_per_step),

@@ -23,6 +23,7 @@
 //
 // Replaces the same reference code as engine.cu (the batch-loop bodies of LightGCN.py:21-29, SimGCL.py:25-36,
 // XSimGCL.py:27-37); world == 1 runs the same sequence without staging or barriers.
+#include <stdlib.h>
 #include "spmm_args.cuh"
 
 namespace srb {
@@ -216,10 +217,20 @@ struct Ctx {
   float* lw(int64_t off) const { return (float*)(loc + off); }
 };
 
+// SRB_SHARD_SYNC=barrier: separate barrier launches between the kernels of a layer instead of waits / signals folded
+// into them (measurement switch; both are kept parity-tested)
+static bool sync_in_kernels() {
+  static const int mode = [] {
+    const char* e = getenv("SRB_SHARD_SYNC");
+    return (e && e[0] == 'b') ? 0 : 1;
+  }();
+  return mode != 0;
+}
+
 // wait / signal folded into the kernels of a layer (PeerSync in spmm_args.cuh)
 static PeerSync peer_sync(const Ctx& c, bool wait, bool signal) {
   PeerSync p = {};
-  if (c.G <= 1) return p;
+  if (c.G <= 1 || !sync_in_kernels()) return p;
   for (int q = 0; q < c.G; ++q) p.flags[q] = (int*)((char*)c.s->sym[q] + c.sp.flags);
   p.epoch = (int*)(c.loc + c.lp.ctrl);
   p.err = p.epoch + 1;
@@ -234,8 +245,11 @@ static PeerSync peer_sync(const Ctx& c, bool wait, bool signal) {
 // wait for the peers' latest signal without sending one (e.g. before adding into rows the peers' reductions store)
 __global__ void shard_wait_kernel(const PeerSync s) { peer_wait(s); }
 
+static int barrier(const Ctx& c);
+
 static int wait_peers(const Ctx& c) {
   if (c.G <= 1) return SRB_OK;
+  if (!sync_in_kernels()) return SRB_OK;  // (barrier mode: every layer already ends with a full barrier)
   shard_wait_kernel<<<1, 32, 0, c.st>>>(peer_sync(c, true, false));
   return post_launch("shard_wait_kernel");
 }
@@ -383,6 +397,7 @@ static int layer(const Ctx& c, const float* xu, const float* xi, const Epi& e) {
   }
   if (c.G == 1) return SRB_OK;
   // ---- item half, part 2: owner-side reduction + epilogue + push to every rank ----
+  if (!sync_in_kernels()) SRB_TRY(barrier(c));
   {
     SpmmArgs a;
     SRB_TRY(base_args(c, s->Rt, c.I, xu, nullptr, a));
@@ -396,7 +411,7 @@ static int layer(const Ctx& c, const float* xu, const float* xi, const Epi& e) {
     a.ps = peer_sync(c, true, true);  // wait: all partials have landed; signal: the finished rows are everywhere
     SRB_TRY(launch_reduce_rows(a, r, c.d, c.st));
   }
-  return SRB_OK;
+  return sync_in_kernels() ? SRB_OK : barrier(c);
 }
 
 // Encoder forward on the sharded tables (R4).  sums: running layer sum / final mean (user local, item owner slice).

@@ -26,27 +26,33 @@ __device__ __forceinline__ int ld_acquire_sys(const int* p) {
   return v;
 }
 
+__device__ __forceinline__ int ld_relaxed_sys(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 __device__ __forceinline__ void peer_wait(const PeerSync& s) {
   if (!s.wait) return;
   if ((int)threadIdx.x < s.world) {
     const int target = *reinterpret_cast<volatile int*>(s.epoch);
     const int* f = s.flags[s.rank] + threadIdx.x;
     const long long t0 = clock64();
-    while (ld_acquire_sys(f) < target) {
+    while (ld_relaxed_sys(f) < target) {  // relaxed polls; one acquire fence once the flag is there
       if (clock64() - t0 > 60000000000ll) {  // ~30 s: a peer died; do not hang the GPU
         *s.err = 1;
         break;
       }
-      __nanosleep(32);
+      __nanosleep(20);
     }
+    __threadfence_system();
   }
   __syncthreads();
 }
 
 __device__ __forceinline__ void peer_signal(const PeerSync& s) {
   if (!s.signal) return;
-  __threadfence_system();  // every thread: its peer stores are ordered before what follows
-  __syncthreads();
+  __syncthreads();  // every store of this CTA has been issued (and is observed by thread 0: its fence is cumulative)
   if (threadIdx.x == 0) {
     __threadfence_system();
     if (atomicAdd(s.counter, 1) == (int)gridDim.x - 1) {  // last CTA of the grid

@@ -1,6 +1,11 @@
 """Launched by torchrun (one rank per GPU) or directly (world 1): the bipartite-sharded step must follow the
-single-GPU fused engine -- same losses, same parameters, same clean forward -- on the same batches and the same
-Philox noise, for XSimGCL, SimGCL and LightGCN, on both peer-store routes (unicast P2P and NVSwitch multicast)."""
+single-GPU fused engine -- same losses, same Adam moments, same clean forward -- on the same batches and the same
+Philox noise, for XSimGCL, SimGCL and LightGCN, on both peer-store routes (unicast P2P and NVSwitch multicast).
+
+Two passes per case.  eps = 0: strict, every compared quantity within 1e-4.  eps as configured: the perturbation
+sign(y) * noise * eps (XSimGCL.py:90-91) is discontinuous at y = 0, so an element within fp32 rounding of zero flips
+under the sharded summation order (item rows are sums of per-rank partial sums); the losses must still agree to
+1e-4 and only a small fraction of rows (the flipped ones and their neighbours) may differ."""
 import os
 import sys
 
@@ -32,12 +37,16 @@ def main():
     for gname, data in graphs.items():
         B = 512
         batches = device_batches(data, B, 3, seed=5)
-        for model, d, L, kw in cases:
-            for mc in routes:
+        for model, d, L, kw0 in cases:
+            for mc, strict in [(m, s) for m in routes for s in ((True, False) if "eps" in kw0 else (True,))]:
+                kw = dict(kw0, eps=0.0) if (strict and "eps" in kw0) else kw0
                 r = sharded_vs_single(model, data, d, L, B, batches, steps=3, multicast=mc, **kw)
-                good = r["max_rel"] <= TOL and r["upd_off_frac"] <= 0.02 and max(r["user_rel"], r["item_rel"]) <= 0.05
+                if strict:
+                    good = r["max_rel"] <= TOL and r["m_rows_off_frac"] == 0.0
+                else:
+                    good = r["loss_rel"] <= TOL and r["m_rows_off_frac"] <= 0.05 and max(r["final_user_rel"], r["final_item_rel"]) <= 0.05
                 if rank == 0:
-                    print(f"{gname} {model} d={d} L={L} route={r['route']}: max_rel {r['max_rel']:.2e} "
+                    print(f"{gname} {model} d={d} L={L} route={r['route']} {'eps=0 strict' if strict and 'eps' in kw0 else 'as configured'}: max_rel {r['max_rel']:.2e} rows off {r['m_rows_off_frac']:.1e} "
                           f"(loss {r['loss_rel']:.1e} m {r['m_user_rel']:.1e}/{r['m_item_rel']:.1e} v {r['v_user_rel']:.1e}/{r['v_item_rel']:.1e} "
                           f"final {r['final_user_rel']:.1e}/{r['final_item_rel']:.1e} params {r['user_rel']:.1e}/{r['item_rel']:.1e} "
                           f"updates off {r['upd_off_frac']:.1e}) {'ok' if good else 'FAIL'}",

@@ -47,6 +47,21 @@ def main():
                 rowmax = (a - b).abs().max(1).values
                 scale = float(b.abs().max())
                 msg.append(f"{name} rel {float(rowmax.max()) / scale:.1e} rows_off {int((rowmax > 1e-4 * scale).sum())}/{a.shape[0]}")
+            if os.environ.get("DIAG_ROWS"):
+                w = pool[k].tolist()
+                b, nu, ni = w[0], w[1], w[2]
+                H = 4
+                uq_u, uq_i = w[H + 3 * B:H + 3 * B + nu], w[H + 4 * B:H + 4 * B + ni]
+                bu, bi, bj = w[H:H + b], w[H + B:H + B + b], w[H + 2 * B:H + 2 * B + b]
+                for name, a, bb, base, uq, secs in (("m_user", sh.mu, ref.m[lo:hi], lo, uq_u, (bu,)), ("m_item", sh.mi[ilo:ihi], ref.m[U + ilo:U + ihi], ilo, uq_i, (bi, bj))):
+                    rowmax = (a - bb).abs().max(1).values
+                    scale = float(bb.abs().max())
+                    off = torch.nonzero(rowmax > 1e-4 * scale).flatten().tolist()[:12]
+                    for r in off:
+                        gid = base + r
+                        pos = uq.index(gid) if gid in uq else -1
+                        cnts = [sec.count(gid) for sec in secs]
+                        print(f"   [rank {rank}] {name} id {gid} pos_in_unique {pos}/{len(uq)} count_in_batch {cnts} diff {float(rowmax[r]):.2e} refmax {float(bb[r].abs().max()):.2e}", flush=True)
             lr = float(((sh.losses - ref.losses).abs() / ref.losses.abs().clamp_min(1e-12)).max())
             print(f"[rank {rank}/{world}] {case} step {k}: " + " | ".join(msg) + f" | loss rel {lr:.1e}", flush=True)
         del sh, ref
