@@ -45,7 +45,7 @@ __device__ __forceinline__ void peer_wait(const PeerSync& s) {
       }
       __nanosleep(20);
     }
-    __threadfence_system();
+    (void)ld_acquire_sys(f);  // relaxed polls, then one acquiring read of the flag that is there
   }
   __syncthreads();
 }
@@ -54,7 +54,7 @@ __device__ __forceinline__ void peer_signal(const PeerSync& s) {
   if (!s.signal) return;
   __syncthreads();  // every store of this CTA has been issued (and is observed by thread 0: its fence is cumulative)
   if (threadIdx.x == 0) {
-    __threadfence_system();
+    __threadfence();  // device scope is enough here: the ONE system-scope fence is the last CTA's, after the counter
     if (atomicAdd(s.counter, 1) == (int)gridDim.x - 1) {  // last CTA of the grid
       *s.counter = 0;
       __threadfence_system();
