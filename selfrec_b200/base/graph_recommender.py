@@ -27,6 +27,8 @@ class GraphRecommender(Recommender):
         self.bestPerformance = []
         self.topN = [int(num) for num in self.ranking]
         self.max_N = max(self.topN)
+        if self.max_N < 1 or self.max_N > self.data.item_num:
+            raise ValueError(f"item.ranking.topN {self.topN}: the longest list must be in 1..item_num={self.data.item_num}")
 
     def print_model_info(self):
         super(GraphRecommender, self).print_model_info()
@@ -70,7 +72,13 @@ class GraphRecommender(Recommender):
             rows = np.stack([np.asarray(self.predict(u), dtype=np.float32) for u in names[s:s + step]])
             for r, uid in enumerate(uids[s:s + step]):
                 rows[r, rated_idx[rated_ptr[uid]:rated_ptr[uid + 1]]] = -10e8
-            ids, sc = ops.topk_rows(torch.from_numpy(rows).cuda(), self.max_N)
+            dev_rows = torch.from_numpy(rows).cuda()
+            parts = []
+            for lo in range(0, self.max_N, ops.TOPK_KERNEL_MAX):  # 32 per pass, winners struck out (ops._score_topk_wide)
+                ids, sc = ops.topk_rows(dev_rows, min(ops.TOPK_KERNEL_MAX, self.max_N - lo))
+                parts.append((ids, sc))
+                dev_rows.scatter_(1, ids.long(), float("-inf"))
+            ids, sc = torch.cat([p[0] for p in parts], 1), torch.cat([p[1] for p in parts], 1)
             ids_out[s:s + step], sc_out[s:s + step] = ids.cpu().numpy(), sc.cpu().numpy()
         return names, ids_out, sc_out
 

@@ -484,6 +484,10 @@ def score_topk(user_emb, item_emb, users, rated_ptr, rated_idx, k, impl=0, stats
     users = _i32(users, dev)
     n_q = users.numel()
     d = user_emb.shape[1]
+    if not 1 <= int(k) <= item_emb.shape[0]:
+        raise SrbError(f"score_topk: k={k} must be in 1..n_items={item_emb.shape[0]} (find_k_largest seeds its heap with the first K candidates)")
+    if k > TOPK_KERNEL_MAX:
+        return _score_topk_wide(user_emb, item_emb, users, rated_ptr, rated_idx, int(k))
     out_ids = torch.empty((n_q, k), device=dev, dtype=torch.int32)
     out_sc = torch.empty((n_q, k), device=dev, dtype=torch.float32)
     desc = _lib.TopkDesc()
@@ -507,6 +511,48 @@ def score_topk(user_emb, item_emb, users, rated_ptr, rated_idx, k, impl=0, stats
     return out_ids, out_sc
 
 
+TOPK_KERNEL_MAX = 32  # list length of the selection kernels (one entry per lane)
+
+
+def _score_topk_wide(user_emb, item_emb, users, rated_ptr, rated_idx, k):
+    """item.ranking.topN above 32 (e.g. 10,20,50): the selection kernels keep 32 entries per user, so the list is
+    extracted 32 at a time from dense score rows -- srb_score_rows (the exact fp32 fma chains of predict()), the rated
+    items masked with -10e8 like graph_recommender.py:48-50, srb_topk_rows, the winners struck out, repeat -- in
+    user blocks of 2048.  Same selection rule (strictly greater replaces the minimum: earliest ids win ties at the
+    cut) and the same order (score descending, ties by id descending) as the single-pass kernels."""
+    dev = user_emb.device
+    n_q, n_items = users.numel(), item_emb.shape[0]
+    out_ids = torch.empty((n_q, k), device=dev, dtype=torch.int32)
+    out_sc = torch.empty((n_q, k), device=dev, dtype=torch.float32)
+    rp = None
+    if rated_ptr is not None:
+        rp, ri = _i32(rated_ptr, dev).long(), _i32(rated_idx, dev).long()
+    for lo in range(0, n_q, 2048):
+        blk = users[lo:lo + 2048]
+        rows = score_rows(user_emb, item_emb, blk)
+        if rp is not None:
+            cnt = rp[blk.long() + 1] - rp[blk.long()]
+            r = torch.repeat_interleave(torch.arange(blk.numel(), device=dev), cnt)
+            c = ri[torch.repeat_interleave(rp[blk.long()], cnt) + (torch.arange(int(cnt.sum()), device=dev) - torch.repeat_interleave(torch.cumsum(cnt, 0) - cnt, cnt))]
+            rows[r, c] = -10e8
+        ids_parts, sc_parts = [], []
+        left = k
+        while left > 0:
+            kk = min(left, TOPK_KERNEL_MAX)
+            ids, sc = topk_rows(rows, kk)
+            ids_parts.append(ids)
+            sc_parts.append(sc)
+            rows.scatter_(1, ids.long(), float("-inf"))
+            left -= kk
+        ids, sc = torch.cat(ids_parts, 1), torch.cat(sc_parts, 1)
+        # one order for the whole list: score descending, ties by id descending (ties may straddle a 32-entry pass)
+        o = torch.sort(ids, dim=1, descending=True, stable=True).indices
+        ids, sc = torch.gather(ids, 1, o), torch.gather(sc, 1, o)
+        o = torch.sort(sc, dim=1, descending=True, stable=True).indices
+        out_ids[lo:lo + 2048], out_sc[lo:lo + 2048] = torch.gather(ids, 1, o), torch.gather(sc, 1, o)
+    return out_ids, out_sc
+
+
 def score_rows(user_emb, item_emb, users):
     """Dense fp32 scores [n_q, n_items] for the listed user ids."""
     lib = _lib.require_device()
@@ -522,6 +568,8 @@ def topk_rows(scores, k):
     lib = _lib.require_device()
     scores = _f32c(scores, "topk scores")
     n_q, n_items = scores.shape
+    if not 1 <= int(k) <= TOPK_KERNEL_MAX:
+        raise SrbError(f"topk_rows: k={k} outside 1..{TOPK_KERNEL_MAX} (score_topk extracts longer lists 32 at a time)")
     out_ids = torch.empty((n_q, k), device=scores.device, dtype=torch.int32)
     out_sc = torch.empty((n_q, k), device=scores.device, dtype=torch.float32)
     _lib.check(lib.srb_topk_rows(_p(scores), n_q, n_items, k, _p(out_ids), _p(out_sc), _stream()), "srb_topk_rows")

@@ -573,3 +573,22 @@ def test_engine_steps_vs_oracle_other_widths_and_partial_batches(torch_cuda, orc
             assert abs(los[2] - ref["cl"]) <= RTOL * abs(ref["cl"]) + 2e-7 / 0.2
         p = got.astype(np.float32).copy()  # continue from the device state: errors do not compound across steps
         m, v = eng.m.cpu().numpy().copy(), eng.v.cpu().numpy().copy()
+
+
+def test_topk_lists_longer_than_the_kernel_width(torch_cuda, orc):
+    """item.ranking.topN up to 100 works like the reference (find_k_largest accepts any K): lists above 32 entries are
+    extracted 32 at a time with the same kernels; ids and scores equal the oracle's."""
+    torch = torch_cuda
+    from selfrec_b200 import ops
+    rng = np.random.default_rng(9)
+    U, I = 40, 700
+    ue = rng.standard_normal((U, 64)).astype(np.float32)
+    ie = rng.standard_normal((I, 64)).astype(np.float32)
+    deg = rng.integers(0, 60, U)
+    ptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int32)
+    idx = np.concatenate([np.sort(rng.choice(I, k, replace=False)) for k in deg]).astype(np.int32)
+    users = np.arange(U, dtype=np.int32)
+    for k in (33, 50, 100):
+        ids, sc = ops.score_topk(torch.from_numpy(ue).cuda(), torch.from_numpy(ie).cuda(), users, ptr, idx, k)
+        oi, os_ = orc.score_topk(ue, ie, users, ptr, idx, k)
+        assert np.array_equal(ids.cpu().numpy(), oi) and np.array_equal(sc.cpu().numpy(), os_), k
