@@ -817,7 +817,7 @@ def run_sharded(args, rank, world, local_rank):
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": WORKLOAD,
-                   "parallelism": f"bipartite-sharded x{world}: users in nnz-balanced blocks (never leave their GPU), item tables replicated; per layer the "
+                   "parallelism": f"bipartite-sharded x{world}: users dealt cyclically (u % world; their rows never leave the GPU), item tables replicated; per layer the "
                                   f"item-side SpMM epilogue stores partial rows into the slice owner's staging area (P2P, reduce-scatter), the owner sums, "
                                   f"applies the epilogue and stores the finished rows to every rank ({route}); 2 device-side barriers per layer; batch losses "
                                   "replicated on a compact [5B, d] table; one srb_shard_step call per step, captured in a CUDA graph",

@@ -127,6 +127,10 @@ typedef struct srb_spmm_desc {
 } srb_spmm_desc;
 
 int srb_spmm_csr(const srb_spmm_desc* desc, void* stream);
+/* The epilogue alone, row by row: Y[r] = epilogue(X[r]) for r < n_rows -- the product with the identity matrix
+ * (rowptr / colidx / vals are not read).  Used for the noise that SimGCL's perturbed encoders add to the shared first
+ * product (SimGCL.py:87-88): same Philox keying / noise tensor indexing as the fused SpMM epilogue. */
+int srb_spmm_epilogue_rows(const srb_spmm_desc* desc, void* stream);
 
 /* Encoder forward (R4).  Composes srb_spmm_csr launches:
  *   LGCN_Encoder.forward LightGCN.py:68-78, SGL_Encoder.forward SGL.py:98-113  (include_ego=1)
@@ -167,6 +171,11 @@ typedef struct srb_encoder_desc {
   float* cl_out;    /* [n, d] or NULL */
   float* work0;
   float* work1;
+  /* optional [n, d]: the output of layer 1 (its noise included), computed by the caller -- SimGCL's three encoders
+   * share the product A * E0 (SimGCL.py:85) and differ only in the noise added to it.  The first product is skipped
+   * and the layer sum starts from x1.  Needs n_layers >= 2, include_ego == 0 and layer_cl != 1; x1 must not be
+   * work0 / work1. */
+  const float* x1;
 } srb_encoder_desc;
 
 int srb_encoder_forward(const srb_encoder_desc* desc, void* stream);
@@ -492,6 +501,12 @@ typedef struct srb_step_desc {
   float* losses;           /* [4] device: rec (bpr), l2, cl (weighted), total */
   void* workspace;
   int64_t workspace_bytes; /* >= srb_step_workspace_bytes */
+  /* optional (all three or none): a cudaStream_t and two cudaEvent_t (timing disabled) owned by the caller, used to run
+   * BPR + L2 beside InfoNCE.  Without them one set per device is shared by every step on that device, which is only
+   * safe while steps on that device are enqueued one after the other. */
+  void* fork_stream;
+  void* fork_event;
+  void* join_event;
 } srb_step_desc;
 
 /* n_hub_work: adj.hub.n_work of the clean graph (chunks of its split rows; 0 when it has none) */
@@ -565,13 +580,13 @@ int srb_spmm_csr_allgather(const srb_spmm_sharded_desc* desc, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Bipartite-sharded training step (selfrec_b200/csrc/sharded.cu).  One process per GPU.
- * Rank g owns the users [user_bounds[g], user_bounds[g+1]) -- their rows of every [U, d] table stay on that GPU --
- * and the item tables are replicated; per propagation layer only the item half is exchanged: each rank's partial
+ * Rank g owns the users u with u % world == g, stored as local row u / world (n_local_users = ceil((n_users - g) / world))
+ * -- their rows of every [U, d] table stay on that GPU -- and the item tables are replicated; per propagation layer only the item half is exchanged: each rank's partial
  * product R_g^T X_u is stored by the SpMM epilogue into the staging area of the rank that owns the item slice
  * (P2P stores, reduce-scatter), the owner adds the partials in rank order, applies the epilogue and stores the
  * finished rows into every rank's copy (all-gather; one multicast store per row when sym_mc is given).  Item slice
  * of rank g: [g * I / world, (g+1) * I / world).
- *   Ru  CSR [n_local_users x n_items]: rows = this rank's users (local ids), columns = item ids
+ *   Ru  CSR [n_local_users x n_items]: rows = this rank's users (local rows), columns = item ids
  *   Rt  CSR [n_items x n_local_users]: its transpose (columns = local user ids); values = the rank's block of the
  *       normalised adjacency (data/graph.py:10-24)
  *   sym[q]   base of rank q's symmetric region (torch.distributed._symmetric_memory), sym_bytes each, zero-filled
@@ -590,7 +605,6 @@ typedef struct srb_shard_desc {
   float l2_div;
   int32_t noise_mode; /* 0 (LightGCN) or 2 */
   uint64_t philox_seed;
-  int32_t user_bounds[9]; /* inner bounds multiples of 32 */
   srb_graph_csr Ru;
   srb_graph_csr Rt;
   const int32_t* batch; /* device batch buffer, identical on every rank */
@@ -617,8 +631,10 @@ typedef struct srb_shard_layout {
   int64_t ctrl;            /* byte offset inside the workspace of int32 {barrier epoch, peer-timeout flag} */
 } srb_shard_layout;
 
+/* hub_chunks_u / hub_chunks_t: Ru.hub.n_work / Rt.hub.n_work of the rank's blocks (capacity of the per-batch split-row
+ * lists of the last forward layer, which is evaluated on the batch rows only) */
 int srb_shard_plan(int32_t n_users, int32_t n_items, int32_t n_local_users, int32_t d, int32_t batch_cap,
-                     int32_t world, srb_shard_layout* out);
+                     int32_t world, int32_t hub_chunks_u, int32_t hub_chunks_t, srb_shard_layout* out);
 int srb_shard_step(const srb_shard_desc* desc, void* stream);
 /* clean forward (evaluation / save(), XSimGCL.py:40-41,53-55): out_user [n_local_users, d]; the complete item half
  * lands in every rank's symmetric region at item_final */

@@ -51,7 +51,7 @@ class EncoderDesc(C.Structure):
         ("layer_cl", C.c_int32), ("noise_mode", C.c_int32), ("noise", VP), ("eps", C.c_float),
         ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64), ("philox_step_dev", VP),
         ("last_rows", VP), ("n_last_rows", C.c_int32), ("last_rows_nv_dev", VP), ("last_rows_hub", HubSplit), ("last_rows_out", VP),
-        ("E0", VP), ("final_out", VP), ("cl_out", VP), ("work0", VP), ("work1", VP),
+        ("E0", VP), ("final_out", VP), ("cl_out", VP), ("work0", VP), ("work1", VP), ("x1", VP),
     ]
 
 
@@ -115,7 +115,7 @@ class StepDesc(C.Structure):
         ("l2_div", C.c_float), ("noise_mode", C.c_int32), ("noise", VP), ("philox_seed", C.c_uint64),
         ("adj", GraphCsr), ("adj_view", GraphCsr * 2), ("batch", VP), ("params", VP), ("adam_m", VP),
         ("adam_v", VP), ("step_dev", VP), ("scalars", VP), ("losses", VP), ("workspace", VP),
-        ("workspace_bytes", C.c_int64),
+        ("workspace_bytes", C.c_int64), ("fork_stream", VP), ("fork_event", VP), ("join_event", VP),
     ]
 
 
@@ -125,7 +125,7 @@ class ShardDesc(C.Structure):
         ("d", C.c_int32), ("n_layers", C.c_int32), ("batch_cap", C.c_int32), ("layer_cl", C.c_int32),
         ("eps", C.c_float), ("tau", C.c_float), ("cl_rate", C.c_float), ("reg", C.c_float),
         ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("adam_eps", C.c_float), ("l2_div", C.c_float),
-        ("noise_mode", C.c_int32), ("philox_seed", C.c_uint64), ("user_bounds", C.c_int32 * 9),
+        ("noise_mode", C.c_int32), ("philox_seed", C.c_uint64),
         ("Ru", GraphCsr), ("Rt", GraphCsr), ("batch", VP), ("pu", VP), ("mu", VP), ("vu", VP), ("mi", VP), ("vi", VP),
         ("step_dev", VP), ("scalars", VP), ("losses", VP), ("sym", VP * 8), ("sym_mc", VP), ("sym_bytes", C.c_int64),
         ("workspace", VP), ("workspace_bytes", C.c_int64),
@@ -152,6 +152,7 @@ SYMBOLS = {
     "srb_launch_count": (C.c_int64, []),
     "srb_device_ok": (C.c_int, []),
     "srb_spmm_csr": (C.c_int, [C.POINTER(SpmmDesc), VP]),
+    "srb_spmm_epilogue_rows": (C.c_int, [C.POINTER(SpmmDesc), VP]),
     "srb_encoder_forward": (C.c_int, [C.POINTER(EncoderDesc), VP]),
     "srb_bpr_l2_fwd_bwd": (C.c_int, [C.POINTER(BprDesc), VP]),
     "srb_infonce_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
@@ -195,7 +196,7 @@ SYMBOLS = {
     "srb_sampler_ring_pop": (C.c_int, [VP, c_i32p]),
     "srb_sampler_ring_stop": (C.c_int, [VP]),
     "srb_spmm_csr_allgather": (C.c_int, [C.POINTER(SpmmShardedDesc), VP]),
-    "srb_shard_plan": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(ShardLayout)]),
+    "srb_shard_plan": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(ShardLayout)]),
     "srb_shard_step": (C.c_int, [C.POINTER(ShardDesc), VP]),
     "srb_shard_forward": (C.c_int, [C.POINTER(ShardDesc), VP, VP]),
 }

@@ -177,6 +177,9 @@ __global__ void __launch_bounds__(256) scatter_add_rows_kernel(float* dst, const
   if (sg.row_hi > sg.row_lo) {  // sharded tables: only the rows this rank owns
     if (row < sg.row_lo || row >= sg.row_hi) return;
     row -= sg.row_lo;
+  } else if (sg.mod > 0) {  // cyclic ownership (bipartite sharding: user u lives on rank u % world, local row u / world)
+    if (row % sg.mod != sg.rem) return;
+    row /= sg.mod;
   }
   for (int c = lane * 4; c < D; c += 128) {
     const float4 v = f4_scale(sg.scale, ldg4(sg.src + (size_t)r * D + c));

@@ -52,6 +52,7 @@ struct ScatterSeg {
   int32_t row_off;
   float scale;
   int32_t row_lo, row_hi;  // optional filter (row_hi > row_lo): only rows[r] + row_off in [row_lo, row_hi), stored at - row_lo
+  int32_t mod, rem;        // optional filter (mod > 0; cyclic row ownership): only rows with row % mod == rem, stored at row / mod
 };
 struct ScatterSegs {
   int count;

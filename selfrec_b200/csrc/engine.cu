@@ -12,6 +12,7 @@
 // gradients G (<= 3B + 2B rows) are kept compact and re-scattered at every level instead of
 // being materialised as dense [N, d] tensors.  SimGCL's three encoders share A, so their
 // three backward chains collapse into one.  The last SpMM applies Adam in its epilogue.
+#include <mutex>
 #include "common.cuh"
 
 namespace srb {
@@ -223,16 +224,28 @@ static int spmm_simple(const srb_step_desc* s, const srb_graph_csr* g, const flo
 // chain applies Adam.  gd_live says whether gd already holds earlier chains' contributions.
 // BPR + L2 and InfoNCE only read the encoder outputs and write disjoint buffers: the step forks BPR onto a
 // side stream (event dependencies, so a stream capture records the fork and join) and joins before the
-// losses are combined.  One side stream + two events per device, created on first use.
+// losses are combined.
 struct ForkRes {
   cudaStream_t side;
   cudaEvent_t fork, join;
   bool ok;
 };
-static ForkRes* fork_res() {
+// Default resources: one side stream + two events per device, created on first use (before any capture: capture()
+// warms up eagerly).  An engine that may run beside another one on the same device brings its own through
+// srb_step_desc.fork_stream / fork_event / join_event, so that two engines never re-record each other's events.
+static ForkRes* fork_res(const srb_step_desc* s, ForkRes* own) {
+  if (s->fork_stream && s->fork_event && s->join_event) {
+    own->side = (cudaStream_t)s->fork_stream;
+    own->fork = (cudaEvent_t)s->fork_event;
+    own->join = (cudaEvent_t)s->join_event;
+    own->ok = true;
+    return own;
+  }
   static ForkRes res[64] = {};
+  static std::mutex mu;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
   ForkRes& r = res[dev];
   if (!r.ok) {
     if (cudaStreamCreateWithFlags(&r.side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
@@ -286,7 +299,7 @@ static ScatterSeg seg(const float* src, const int32_t* rows, const int32_t* n_de
 }
 
 static int encoder(const srb_step_desc* s, const Ws& w, const srb_graph_csr* g, bool include_ego, int noise_mode, int view,
-                   int layer_cl, float* final_out, float* cl_out, cudaStream_t st) {
+                   int layer_cl, float* final_out, float* cl_out, cudaStream_t st, const float* x1 = nullptr) {
   // training forward: the final mean is only read at the batch rows, so the last layer skips the rest
   srb_encoder_desc e = {};
   e.rowptr = g->rowptr;
@@ -321,7 +334,31 @@ static int encoder(const srb_step_desc* s, const Ws& w, const srb_graph_csr* g, 
   e.cl_out = cl_out;
   e.work0 = w.work0;
   e.work1 = w.work1;
+  e.x1 = x1;
   return srb_encoder_forward(&e, st);
+}
+
+// out = x + sign(x) * normalize(noise) * eps, row by row: the noise one perturbed SimGCL encoder adds to the shared
+// first product (SimGCL.py:87-88), drawn exactly as the fused SpMM epilogue of layer 1 of view `view` would draw it.
+static int perturb_rows(const srb_step_desc* s, const float* x, float* out, int view, cudaStream_t st) {
+  const size_t nd = (size_t)(s->n_users + s->n_items) * s->d;
+  srb_spmm_desc p = {};
+  p.rowptr = s->adj.rowptr;  // (not read by the epilogue-only kernel)
+  p.colidx = s->adj.colidx;
+  p.vals = s->adj.vals;
+  p.n_rows = p.n_cols = s->n_users + s->n_items;
+  p.d = s->d;
+  p.X = x;
+  p.Y = out;
+  p.extra_scale = 1.f;
+  p.sum_scale = 1.f;
+  p.noise_mode = s->noise_mode;
+  if (s->noise_mode == 1) p.noise = s->noise + (size_t)view * s->n_layers * nd;
+  p.eps = s->eps;
+  p.philox_seed = s->philox_seed;
+  p.philox_offset = ((uint64_t)view << 32) | 0x10u;
+  p.philox_step_dev = s->step_dev;
+  return srb_spmm_epilogue_rows(&p, st);
 }
 
 }  // namespace srb
@@ -391,9 +428,20 @@ extern "C" int srb_train_step(const srb_step_desc* s, void* stream) {
     case SRB_MODEL_SIMGCL:
       SRB_REQUIRE(s->noise_mode == 1 || s->noise_mode == 2, "step: SimGCL needs noise_mode 1 or 2");
       SRB_REQUIRE(s->noise_mode != 1 || s->noise, "step: noise tensor missing");
-      SRB_TRY(encoder(s, w, &s->adj, false, 0, 0, 0, w.final_, nullptr, st));
-      SRB_TRY(encoder(s, w, &s->adj, false, s->noise_mode, 0, 0, w.cl, nullptr, st));
-      SRB_TRY(encoder(s, w, &s->adj, false, s->noise_mode, 1, 0, w.v2, nullptr, st));
+      if (L >= 2) {
+        // layer 1 of the three encoders is the same product A * E0 (SimGCL.py:85); only the noise added to it differs
+        // (:87-88).  It is evaluated once; acc0 / acc1 / gd belong to the backward pass and are free until then.
+        SRB_TRY(spmm_simple(s, &s->adj, s->params, w.acc0, nullptr, false, st));
+        SRB_TRY(perturb_rows(s, w.acc0, w.acc1, 0, st));
+        SRB_TRY(perturb_rows(s, w.acc0, w.gd, 1, st));
+        SRB_TRY(encoder(s, w, &s->adj, false, 0, 0, 0, w.final_, nullptr, st, w.acc0));
+        SRB_TRY(encoder(s, w, &s->adj, false, s->noise_mode, 0, 0, w.cl, nullptr, st, w.acc1));
+        SRB_TRY(encoder(s, w, &s->adj, false, s->noise_mode, 1, 0, w.v2, nullptr, st, w.gd));
+      } else {
+        SRB_TRY(encoder(s, w, &s->adj, false, 0, 0, 0, w.final_, nullptr, st));
+        SRB_TRY(encoder(s, w, &s->adj, false, s->noise_mode, 0, 0, w.cl, nullptr, st));
+        SRB_TRY(encoder(s, w, &s->adj, false, s->noise_mode, 1, 0, w.v2, nullptr, st));
+      }
       table = w.final_;
       break;
     case SRB_MODEL_SGL:
@@ -406,7 +454,8 @@ extern "C" int srb_train_step(const srb_step_desc* s, void* stream) {
   }
 
   // ---- BPR + L2 (on the side stream when an InfoNCE follows) ----
-  ForkRes* fk = (s->model == SRB_MODEL_XSIMGCL || s->model == SRB_MODEL_SIMGCL || s->model == SRB_MODEL_SGL) ? fork_res() : nullptr;
+  ForkRes fk_own = {};
+  ForkRes* fk = (s->model == SRB_MODEL_XSIMGCL || s->model == SRB_MODEL_SIMGCL || s->model == SRB_MODEL_SGL) ? fork_res(s, &fk_own) : nullptr;
   if (fk) {
     SRB_TRY(check_cuda(cudaEventRecord(fk->fork, st), "fork record"));
     SRB_TRY(check_cuda(cudaStreamWaitEvent(fk->side, fk->fork, 0), "fork wait"));

@@ -1,8 +1,11 @@
 // Bipartite-sharded training step, one process per GPU, no NCCL on the data path.
 //
-// The normalised adjacency is  A = [[0, R], [R^T, 0]]  (users x items block R).  Rank g owns a contiguous,
-// nnz-balanced block of USERS -- their rows of every [U, d] table (parameters, moments, layer buffers) never leave
-// the GPU -- while the (5-50x smaller) ITEM tables are replicated.  One propagation layer is
+// The normalised adjacency is  A = [[0, R], [R^T, 0]]  (users x items block R).  Rank g owns the USERS u with
+// u % world == g (local row u / world): their rows of every [U, d] table (parameters, moments, layer buffers) never
+// leave the GPU.  The cyclic assignment gives every rank the same mix of heavy and light users -- ids follow first
+// appearance in the training file (ui_graph.py:29-40), so on a power-law graph contiguous nnz-balanced blocks put a
+// few hundred hub users on rank 0 and millions of cold ones on the last rank, whose products then take 1.5x longer
+// (profiles/r02l_trace_10M_n2_barrier.txt).  The (5-50x smaller) ITEM tables are replicated.  One propagation layer is
 //     X_u' [block g] = R_g  X_i                 local SpMM over the replicated item table, nothing to exchange
 //     X_i'           = sum_g R_g^T X_u[block g]  every rank contributes a partial [I, d] product
 // and only the item half crosses NVLink: the item-side SpMM stores each finished partial row straight into the
@@ -61,14 +64,73 @@ __global__ void shard_barrier_kernel(const BarrierArgs b) {
   }
 }
 
-// bits of the batch's users / items (masks of the row-sparse first backward product)
-__global__ void __launch_bounds__(256) shard_masks_kernel(const int32_t* batch, int cap, uint32_t* umask, uint32_t* imask) {
+// Bits of the batch's (local) users / items (masks of the row-sparse first backward product: umask over this rank's
+// local user rows, imask over all items), and -- from the thread that sets
+// a bit first, so every row is listed once -- the batch's rows of this rank's two blocks, classified by degree for the
+// last forward layer (nothing but the batch rows of the final mean is read): local users -> rows of Ru, items ->
+// rows of Rt.  Lists follow srb_spmm_desc.n_vlong_dev: four segments (split, CTA, warp, lane group -- unused) of
+// capacity cap (users) / 2 * cap (items); cnt[0..3] class sizes and cnt[4] chunks of the user list, cnt[8..] of the
+// item list.  cnt and both bitmaps are zeroed by the caller.
+struct BatchRowsArgs {
+  const int32_t* batch;
+  int cap;
+  uint32_t* umask;
+  uint32_t* imask;
+  int world, rank;   // user u lives on rank u % world as local row u / world
+  const int32_t* ru_rowptr;
+  const int32_t* rt_rowptr;
+  int32_t* rows_u;    // [4][cap]
+  int32_t* rows_i;    // [4][2 * cap]
+  int32_t* cnt;       // [16]
+  int32_t* hfirst_u;  // [cap] or null (no split rows in Ru)
+  int32_t* hwork_u;   // [hcap_u][2]
+  int hcap_u;
+  int32_t* hfirst_i;  // [2 * cap] or null
+  int32_t* hwork_i;
+  int hcap_i;
+};
+
+__global__ void __launch_bounds__(256) shard_batch_rows_kernel(const BatchRowsArgs a) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int b = min(batch[0], cap);
-  const int sec = t / cap, k = t % cap;
+  const int b = min(a.batch[0], a.cap);
+  const int sec = t / a.cap, k = t % a.cap;
   if (sec >= 3 || k >= b) return;
-  const int id = batch[SRB_BATCH_HEADER + sec * cap + k];
-  atomicOr((sec == 0 ? umask : imask) + (id >> 5), 1u << (id & 31));
+  const int id = a.batch[SRB_BATCH_HEADER + sec * a.cap + k];
+  const bool user = sec == 0;
+  int row = id;
+  if (user) {
+    if (id % a.world != a.rank) return;  // another rank's user
+    row = id / a.world;
+  }
+  const uint32_t bit = 1u << (row & 31);
+  if (atomicOr((user ? a.umask : a.imask) + (row >> 5), bit) & bit) return;  // listed already
+  const int32_t* rowptr = user ? a.ru_rowptr : a.rt_rowptr;
+  int32_t* rows = user ? a.rows_u : a.rows_i;
+  int32_t* counters = a.cnt + (user ? 0 : 8);
+  int32_t* hfirst = user ? a.hfirst_u : a.hfirst_i;
+  int32_t* hwork = user ? a.hwork_u : a.hwork_i;
+  const int hcap = user ? a.hcap_u : a.hcap_i;
+  const int capr = user ? a.cap : 2 * a.cap;
+  const int deg = rowptr[row + 1] - rowptr[row];
+  // few rows: parallelism is scarce, so no row shares a warp and rows above 4 warp-iterations get a CTA
+  const int cls = (hfirst && deg >= SRB_HUB_MIN_NNZ) ? 0 : (deg >= 128 ? 1 : 2);
+  const unsigned mine = __match_any_sync(__activemask(), cls + (user ? 0 : 4));
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(mine) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(counters + cls, __popc(mine));
+  base = __shfl_sync(mine, base, leader);
+  const int slot = base + __popc(mine & ((1u << lane) - 1));
+  rows[cls * capr + slot] = row;
+  if (cls == 0) {
+    const int nch = (deg + SRB_HUB_CHUNK - 1) / SRB_HUB_CHUNK;
+    const int first = atomicAdd(counters + 4, nch);
+    hfirst[slot] = first;
+    for (int q = 0; q < nch && first + q < hcap; ++q) {
+      hwork[2 * (first + q)] = row;
+      hwork[2 * (first + q) + 1] = q;
+    }
+  }
 }
 
 // compact table of the rows a batch reads: slot = section * cap + k (sections: u, i, j, unique u, unique i).
@@ -79,7 +141,7 @@ struct GatherArgs {
   int sec_lo, sec_hi;
   const float* utab;  // [n_local_users, D] local
   const float* itab;  // [n_items, D] (owned slice valid)
-  int ub, ub_end, ib, ib_end;
+  int world, rank, ib, ib_end;
   float* dst[8];
   int n_dst;
   int32_t* ar;  // [2*cap]: k and cap + k (index lists of the compact tables), written by block 0
@@ -100,8 +162,8 @@ __global__ void __launch_bounds__(256) shard_gather_kernel(const GatherArgs a) {
   const bool user = (sec == 0 || sec == 3);
   const float* src;
   if (user) {
-    if (id < a.ub || id >= a.ub_end) return;
-    src = a.utab + (size_t)(id - a.ub) * D;
+    if (id % a.world != a.rank) return;
+    src = a.utab + (size_t)(id / a.world) * D;
   } else {
     if (id < a.ib || id >= a.ib_end) return;
     src = a.itab + (size_t)id * D;
@@ -164,11 +226,12 @@ struct LocalPlan {
   int64_t ctrl;  // [0] barrier epoch, [1] error flag (zeroed once by the host, never by a step)
   int64_t xu[2], su, clu, v2u, au[2], gdu;
   int64_t v2_i, gdi;
-  int64_t g_emb, g_l2, g_nce, bpr_scratch, bpr_losses, nce_losses, ar, umask, imask, nce_ws, total;
+  int64_t g_emb, g_l2, g_nce, bpr_scratch, bpr_losses, nce_losses, ar, umask, imask, cnt, nce_ws, total;
+  int64_t rows_u, rows_i, hfirst_u, hfirst_i, hwork_u, hwork_i;  // batch-row lists of the last forward layer
   int64_t nce_ws_bytes;
 };
 
-static LocalPlan local_plan(int64_t U, int64_t I, int64_t Ug, int64_t d, int64_t B) {
+static LocalPlan local_plan(int64_t U, int64_t I, int64_t Ug, int64_t d, int64_t B, int64_t hub_u, int64_t hub_t) {
   LocalPlan p;
   int64_t off = 0;
   auto take = [&](int64_t bytes) {
@@ -195,11 +258,18 @@ static LocalPlan local_plan(int64_t U, int64_t I, int64_t Ug, int64_t d, int64_t
   p.bpr_losses = take(2 * 4);
   p.nce_losses = take(4 * 4);
   p.ar = take(2 * B * 4);
-  // one memset clears both bitmaps
-  p.umask = take(((U + 31) / 32) * 4);
+  // one memset clears both bitmaps and the list counters
+  p.umask = take(((Ug + 31) / 32) * 4 + 4);  // bitmap over this rank's local user rows
   p.imask = take(((I + 31) / 32) * 4);
+  p.cnt = take(16 * 4);
   p.nce_ws_bytes = srb_infonce_workspace_bytes((int32_t)B, (int32_t)d, 2);
   p.nce_ws = take(p.nce_ws_bytes);
+  p.rows_u = take(4 * B * 4);
+  p.rows_i = take(4 * 2 * B * 4);
+  p.hfirst_u = take(B * 4);
+  p.hfirst_i = take(2 * B * 4);
+  p.hwork_u = take(hub_u * 2 * 4);
+  p.hwork_i = take(hub_t * 2 * 4);
   p.total = off;
   return p;
 }
@@ -209,7 +279,7 @@ struct Ctx {
   SymPlan sp;
   LocalPlan lp;
   cudaStream_t st;
-  int G, rank, U, I, Ug, ub, ib, ib_end, d, L, B;
+  int G, rank, U, I, Ug, ib, ib_end, d, L, B;
   char* sym;   // local symmetric region
   char* loc;   // local workspace
   float* symf(int64_t off, int q) const { return (float*)((char*)s->sym[q] + off); }
@@ -284,6 +354,7 @@ struct Epi {
   bool adam = false;
   const uint32_t* mask_u = nullptr;  // bitmap over this rank's users (columns of Rt)
   const uint32_t* mask_i = nullptr;  // bitmap over items (columns of Ru)
+  bool rows_only = false;            // last forward layer: only the batch rows (lists of shard_batch_rows_kernel)
 };
 
 static int base_args(const Ctx& c, const srb_graph_csr& g, int n_rows, const float* X, const uint32_t* mask, SpmmArgs& a) {
@@ -303,6 +374,23 @@ static int base_args(const Ctx& c, const srb_graph_csr& g, int n_rows, const flo
   p.extra_scale = 1.f;
   p.sum_scale = 1.f;
   return fill_args(&p, a);
+}
+
+// Restrict a product over one of the rank's blocks to the batch rows listed by shard_batch_rows_kernel
+// (device-classified list, dynamic chunk lists of the split rows; the graph's own partial-sum scratch is reused).
+static void use_batch_rows(const Ctx& c, bool item_side, SpmmArgs& a) {
+  const srb_graph_csr& g = item_side ? c.s->Rt : c.s->Ru;
+  const int hcap = g.hub.n_work;
+  a.row_order = (const int32_t*)(c.loc + (item_side ? c.lp.rows_i : c.lp.rows_u));
+  a.n_rows = item_side ? 2 * c.B : c.B;
+  a.n_vlong_dev = (const int32_t*)(c.loc + c.lp.cnt) + (item_side ? 8 : 0);
+  a.n_huge = a.n_vlong = a.n_long = 0;
+  a.hub_first = hcap ? (const int32_t*)(c.loc + (item_side ? c.lp.hfirst_i : c.lp.hfirst_u)) : nullptr;
+  a.hub_work = hcap ? (const int32_t*)(c.loc + (item_side ? c.lp.hwork_i : c.lp.hwork_u)) : nullptr;
+  a.hub_part = hcap ? g.hub.part : nullptr;
+  a.n_work = hcap;
+  a.seg = a.seg_cnt = a.order_cta = a.order_warp = nullptr;
+  a.n_cta = a.n_warp = 0;
 }
 
 static void epi_common(const Ctx& c, const Epi& e, SpmmArgs& a) {
@@ -364,6 +452,7 @@ static int layer(const Ctx& c, const float* xu, const float* xi, const Epi& e) {
   {
     SpmmArgs a;
     SRB_TRY(base_args(c, s->Rt, c.I, xu, e.mask_u, a));
+    if (e.rows_only) use_batch_rows(c, true, a);
     if (c.G == 1) {
       item_epilogue(c, e, a);
     } else {
@@ -381,8 +470,10 @@ static int layer(const Ctx& c, const float* xu, const float* xi, const Epi& e) {
   if (c.Ug > 0) {
     SpmmArgs a;
     SRB_TRY(base_args(c, s->Ru, c.Ug, xi, e.mask_i, a));
+    if (e.rows_only) use_batch_rows(c, false, a);
     epi_common(c, e, a);
-    a.noise_row_base = c.ub;
+    a.noise_row_base = c.rank;  // global id of local user row r: rank + r * world
+    a.noise_row_stride = c.G;
     a.row_begin = 0;
     a.Y = e.y_u;
     a.extra = e.extra_u;
@@ -408,6 +499,7 @@ static int layer(const Ctx& c, const float* xu, const float* xi, const Epi& e) {
     r.stage_cap = c.sp.stage_cap;
     r.slice_begin = c.ib;
     r.n_slice = c.ib_end - c.ib;
+    r.mask = e.rows_only ? (const uint32_t*)(c.loc + c.lp.imask) : nullptr;
     a.ps = peer_sync(c, true, true);  // wait: all partials have landed; signal: the finished rows are everywhere
     SRB_TRY(launch_reduce_rows(a, r, c.d, c.st));
   }
@@ -415,15 +507,18 @@ static int layer(const Ctx& c, const float* xu, const float* xi, const Epi& e) {
 }
 
 // Encoder forward on the sharded tables (R4).  sums: running layer sum / final mean (user local, item owner slice).
+// batch_rows: training forward -- the final mean is only read at the batch rows, so the last layer skips the rest.
+// x1u / x1i: output of layer 1 evaluated by the caller (SimGCL's shared first product); the loop starts at layer 2.
 static int encoder(const Ctx& c, bool include_ego, int noise_mode, int view, int layer_cl, float* sum_u, float* sum_i,
-                   float* cl_u, int64_t cl_i_off, bool push_final_items) {
+                   float* cl_u, int64_t cl_i_off, bool push_final_items, bool batch_rows, const float* x1u = nullptr,
+                   const float* x1i = nullptr) {
   const srb_shard_desc* s = c.s;
   const int L = c.L;
   const float inv = 1.0f / (float)(include_ego ? L + 1 : L);
-  const float* xu = s->pu;
-  const float* xi = c.mine(c.sp.pi);
+  const float* xu = x1u ? x1u : s->pu;
+  const float* xi = x1u ? x1i : c.mine(c.sp.pi);
   int pp = 0;
-  for (int k = 0; k < L; ++k) {
+  for (int k = x1u ? 1 : 0; k < L; ++k) {
     const bool last = k == L - 1;
     const bool is_cl = cl_u && layer_cl == k + 1;
     Epi e;
@@ -437,11 +532,12 @@ static int encoder(const Ctx& c, bool include_ego, int noise_mode, int view, int
       e.y_i = c.sp.xi[pp];
       pp ^= 1;
     }
-    e.sum_in_u = k == 0 ? (include_ego ? s->pu : nullptr) : sum_u;
-    e.sum_in_i = k == 0 ? (include_ego ? c.mine(c.sp.pi) : nullptr) : sum_i;
+    e.sum_in_u = k == 0 ? (include_ego ? s->pu : nullptr) : ((k == 1 && x1u) ? x1u : sum_u);
+    e.sum_in_i = k == 0 ? (include_ego ? c.mine(c.sp.pi) : nullptr) : ((k == 1 && x1u) ? x1i : sum_i);
     e.sum_out_u = sum_u;
     e.sum_out_i = sum_i;
     e.sum_scale = last ? inv : 1.f;
+    e.rows_only = batch_rows && last && !is_cl;  // (a CL view at the last layer is needed in full)
     if (last && push_final_items) e.sum_push_i = (int64_t)((char*)sum_i - c.sym);
     SRB_TRY(layer(c, xu, xi, e));
     if (e.y_u) {
@@ -460,8 +556,8 @@ static int gather(const Ctx& c, const float* utab, const float* itab, int64_t ct
   g.sec_hi = sec_hi;
   g.utab = utab;
   g.itab = itab;
-  g.ub = c.ub;
-  g.ub_end = c.ub + c.Ug;
+  g.world = c.G;
+  g.rank = c.rank;
   g.ib = c.ib;
   g.ib_end = c.ib_end;
   for (int q = 0; q < c.G; ++q) g.dst[q] = c.symf(ctab_off, q);
@@ -478,7 +574,7 @@ static int gather(const Ctx& c, const float* utab, const float* itab, int64_t ct
 }
 
 static ScatterSeg useg(const Ctx& c, const float* src, const int32_t* rows, const int32_t* n_dev, float scale) {
-  ScatterSeg g = {src, rows, n_dev, c.B, 0, scale, c.ub, c.ub + c.Ug};
+  ScatterSeg g = {src, rows, n_dev, c.B, 0, scale, 0, 0, c.G, c.rank};
   return g;
 }
 static ScatterSeg iseg(const Ctx& c, const float* src, const int32_t* rows, const int32_t* n_dev, float scale) {
@@ -494,12 +590,7 @@ static int make_ctx(const srb_shard_desc* s, void* stream, Ctx& c) {
   SRB_REQUIRE(s->d == 32 || s->d == 64 || s->d == 128, "shard: unsupported d=%d (32, 64, 128)", s->d);
   SRB_REQUIRE(s->n_users > 0 && s->n_items > 0 && s->batch_cap > 0 && s->n_layers >= 1, "shard: bad sizes");
   SRB_REQUIRE(s->noise_mode == 0 || s->noise_mode == 2, "shard: noise comes from the in-kernel Philox stream (noise_mode 2)");
-  SRB_REQUIRE(s->user_bounds[0] == 0 && s->user_bounds[s->world] == s->n_users, "shard: user_bounds must cover [0, n_users)");
-  for (int g = 0; g < s->world; ++g) {
-    SRB_REQUIRE(s->user_bounds[g] <= s->user_bounds[g + 1], "shard: user_bounds must ascend");
-    SRB_REQUIRE(g == 0 || (s->user_bounds[g] & 31) == 0, "shard: inner user bounds must be multiples of 32");
-    SRB_REQUIRE(s->sym[g] != nullptr, "shard: null symmetric region of rank %d", g);
-  }
+  for (int g = 0; g < s->world; ++g) SRB_REQUIRE(s->sym[g] != nullptr, "shard: null symmetric region of rank %d", g);
   SRB_REQUIRE(s->Ru.rowptr && s->Ru.colidx && s->Ru.vals && s->Rt.rowptr && s->Rt.colidx && s->Rt.vals, "shard: null matrix");
   SRB_REQUIRE(s->pu && s->mu && s->vu && s->mi && s->vi && s->step_dev && s->scalars && s->losses, "shard: null pointer");
   c.s = s;
@@ -508,8 +599,7 @@ static int make_ctx(const srb_shard_desc* s, void* stream, Ctx& c) {
   c.rank = s->rank;
   c.U = s->n_users;
   c.I = s->n_items;
-  c.ub = s->user_bounds[s->rank];
-  c.Ug = s->user_bounds[s->rank + 1] - c.ub;
+  c.Ug = (s->n_users - s->rank + s->world - 1) / s->world;  // users rank, rank + world, rank + 2 world, ...
   c.ib = (int)((int64_t)s->rank * c.I / c.G);
   c.ib_end = (int)((int64_t)(s->rank + 1) * c.I / c.G);
   SRB_REQUIRE(c.Ug > 0, "shard: rank %d owns no users", s->rank);
@@ -517,7 +607,7 @@ static int make_ctx(const srb_shard_desc* s, void* stream, Ctx& c) {
   c.L = s->n_layers;
   c.B = s->batch_cap;
   c.sp = sym_plan(c.I, c.d, c.B, c.G);
-  c.lp = local_plan(c.U, c.I, c.Ug, c.d, c.B);
+  c.lp = local_plan(c.U, c.I, c.Ug, c.d, c.B, s->Ru.hub.n_work, s->Rt.hub.n_work);
   SRB_REQUIRE(s->sym_bytes >= c.sp.total, "shard: symmetric region too small (%lld < %lld)", (long long)s->sym_bytes, (long long)c.sp.total);
   SRB_REQUIRE(s->workspace && s->workspace_bytes >= c.lp.total, "shard: workspace too small (%lld < %lld)",
               (long long)s->workspace_bytes, (long long)c.lp.total);
@@ -530,10 +620,11 @@ static int make_ctx(const srb_shard_desc* s, void* stream, Ctx& c) {
 }  // namespace srb
 
 extern "C" int srb_shard_plan(int32_t n_users, int32_t n_items, int32_t n_local_users, int32_t d, int32_t batch_cap, int32_t world,
-                                srb_shard_layout* out) {
-  SRB_REQUIRE(out && world >= 1 && world <= 8 && n_items > 0 && d > 0 && batch_cap > 0, "shard_plan: bad arguments");
+                                int32_t hub_chunks_u, int32_t hub_chunks_t, srb_shard_layout* out) {
+  SRB_REQUIRE(out && world >= 1 && world <= 8 && n_items > 0 && d > 0 && batch_cap > 0 && hub_chunks_u >= 0 && hub_chunks_t >= 0,
+              "shard_plan: bad arguments");
   const srb::SymPlan sp = srb::sym_plan(n_items, d, batch_cap, world);
-  const srb::LocalPlan lp = srb::local_plan(n_users, n_items, n_local_users, d, batch_cap);
+  const srb::LocalPlan lp = srb::local_plan(n_users, n_items, n_local_users, d, batch_cap, hub_chunks_u, hub_chunks_t);
   out->sym_bytes = sp.total;
   out->workspace_bytes = lp.total;
   out->item_params = sp.pi;
@@ -563,8 +654,28 @@ extern "C" int srb_shard_step(const srb_shard_desc* s, void* stream) {
   uint32_t* umask = (uint32_t*)(c.loc + c.lp.umask);
   uint32_t* imask = (uint32_t*)(c.loc + c.lp.imask);
   SRB_TRY(check_cuda(cudaMemsetAsync(umask, 0, (size_t)(c.lp.nce_ws - c.lp.umask), st), "shard mask memset"));
-  shard_masks_kernel<<<(3 * B + 255) / 256, 256, 0, st>>>(s->batch, B, umask, imask);
-  SRB_TRY(post_launch("shard_masks_kernel"));
+  {
+    BatchRowsArgs br = {};
+    br.batch = s->batch;
+    br.cap = B;
+    br.umask = umask;
+    br.imask = imask;
+    br.world = c.G;
+    br.rank = c.rank;
+    br.ru_rowptr = s->Ru.rowptr;
+    br.rt_rowptr = s->Rt.rowptr;
+    br.rows_u = (int32_t*)(c.loc + c.lp.rows_u);
+    br.rows_i = (int32_t*)(c.loc + c.lp.rows_i);
+    br.cnt = (int32_t*)(c.loc + c.lp.cnt);
+    br.hcap_u = s->Ru.hub.n_work;
+    br.hcap_i = s->Rt.hub.n_work;
+    br.hfirst_u = br.hcap_u ? (int32_t*)(c.loc + c.lp.hfirst_u) : nullptr;
+    br.hwork_u = (int32_t*)(c.loc + c.lp.hwork_u);
+    br.hfirst_i = br.hcap_i ? (int32_t*)(c.loc + c.lp.hfirst_i) : nullptr;
+    br.hwork_i = (int32_t*)(c.loc + c.lp.hwork_i);
+    shard_batch_rows_kernel<<<(3 * B + 255) / 256, 256, 0, st>>>(br);
+    SRB_TRY(post_launch("shard_batch_rows_kernel"));
+  }
 
   // ---- forward ----
   float* su = c.lw(c.lp.su);
@@ -574,13 +685,51 @@ extern "C" int srb_shard_step(const srb_shard_desc* s, void* stream) {
   float* v2i = c.lw(c.lp.v2_i);
   const bool cl_hit = xs && s->layer_cl >= 1 && s->layer_cl <= L;
   if (lg) {
-    SRB_TRY(encoder(c, true, 0, 0, 0, su, si, nullptr, -1, false));
+    SRB_TRY(encoder(c, true, 0, 0, 0, su, si, nullptr, -1, false, true));
   } else if (xs) {
-    SRB_TRY(encoder(c, false, 2, 0, cl_hit ? s->layer_cl : 0, su, si, cl_hit ? clu : nullptr, c.sp.cl_i, false));
+    SRB_TRY(encoder(c, false, 2, 0, cl_hit ? s->layer_cl : 0, su, si, cl_hit ? clu : nullptr, c.sp.cl_i, false, true));
+  } else if (L >= 2) {
+    // layer 1 of SimGCL's three encoders is the same product (SimGCL.py:85): evaluated once into the backward
+    // buffers (free until the backward pass), then perturbed per view (:87-88) -- users locally, the replicated
+    // item table on every rank (the Philox stream is keyed by global row id: all replicas agree)
+    float* zu = c.lw(c.lp.au[0]);
+    float* zi = c.mine(c.sp.ai[0]);
+    float* x1u[2] = {c.lw(c.lp.au[1]), c.lw(c.lp.gdu)};
+    float* x1i[2] = {c.mine(c.sp.ai[1]), c.lw(c.lp.gdi)};
+    {
+      Epi e;
+      e.y_u = zu;
+      e.y_i = c.sp.ai[0];
+      SRB_TRY(layer(c, s->pu, c.mine(c.sp.pi), e));
+      SRB_TRY(wait_peers(c));  // every slice of the item half has arrived
+    }
+    for (int v = 0; v < 2; ++v) {
+      Epi e;
+      e.noise_mode = 2;
+      e.poff = ((uint64_t)v << 32) | 0x10u;
+      if (c.Ug > 0) {
+        SpmmArgs a;
+        SRB_TRY(base_args(c, s->Ru, c.Ug, zu, nullptr, a));
+        epi_common(c, e, a);
+        a.noise_row_base = c.rank;
+        a.noise_row_stride = c.G;
+        a.Y = x1u[v];
+        SRB_TRY(launch_rows_epilogue(a, c.d, st));
+      }
+      SpmmArgs a;
+      SRB_TRY(base_args(c, s->Rt, c.I, zi, nullptr, a));
+      epi_common(c, e, a);
+      a.noise_row_base = c.U;
+      a.Y = x1i[v];
+      SRB_TRY(launch_rows_epilogue(a, c.d, st));
+    }
+    SRB_TRY(encoder(c, false, 0, 0, 0, su, si, nullptr, -1, false, true, zu, zi));
+    SRB_TRY(encoder(c, false, 2, 0, 0, clu, c.mine(c.sp.cl_i), nullptr, -1, false, true, x1u[0], x1i[0]));
+    SRB_TRY(encoder(c, false, 2, 1, 0, v2u, v2i, nullptr, -1, false, true, x1u[1], x1i[1]));
   } else {
-    SRB_TRY(encoder(c, false, 0, 0, 0, su, si, nullptr, -1, false));
-    SRB_TRY(encoder(c, false, 2, 0, 0, clu, c.mine(c.sp.cl_i), nullptr, -1, false));
-    SRB_TRY(encoder(c, false, 2, 1, 0, v2u, v2i, nullptr, -1, false));
+    SRB_TRY(encoder(c, false, 0, 0, 0, su, si, nullptr, -1, false, true));
+    SRB_TRY(encoder(c, false, 2, 0, 0, clu, c.mine(c.sp.cl_i), nullptr, -1, false, true));
+    SRB_TRY(encoder(c, false, 2, 1, 0, v2u, v2i, nullptr, -1, false, true));
   }
 
   // ---- the rows the batch reads -> compact tables on every rank ----
@@ -690,7 +839,7 @@ extern "C" int srb_shard_step(const srb_shard_desc* s, void* stream) {
     e.y_u = au[x ^ 1];
     e.y_i = c.sp.ai[x ^ 1];
     if (k == L - 1) {  // the seed is non-zero at the batch rows only
-      e.mask_u = umask + (c.ub >> 5);
+      e.mask_u = umask;
       e.mask_i = imask;
     }
     SRB_TRY(layer(c, au[x], c.mine(c.sp.ai[x]), e));
@@ -713,7 +862,7 @@ extern "C" int srb_shard_step(const srb_shard_desc* s, void* stream) {
   e.extra_u = ego_add ? gdu : nullptr;
   e.extra_i = ego_add ? gdi : nullptr;
   if (L == 1) {
-    e.mask_u = umask + (c.ub >> 5);
+    e.mask_u = umask;
     e.mask_i = imask;
   }
   return layer(c, au[x], c.mine(c.sp.ai[x]), e);
@@ -728,6 +877,6 @@ extern "C" int srb_shard_forward(const srb_shard_desc* s, float* out_user, void*
   SRB_TRY(make_ctx(s, stream, c));
   SRB_REQUIRE(out_user != nullptr || c.Ug == 0, "shard_forward: null output");
   const bool ego = s->model == SRB_MODEL_LIGHTGCN;
-  SRB_TRY(encoder(c, ego, 0, 0, 0, out_user, c.mine(c.sp.fin_i), nullptr, -1, true));
+  SRB_TRY(encoder(c, ego, 0, 0, 0, out_user, c.mine(c.sp.fin_i), nullptr, -1, true, false));
   return wait_peers(c);  // every slice of the item output has arrived
 }

@@ -6,6 +6,7 @@
 //
 // HBM/L2-bound integer + fp32 work: no tensor cores here by design (see the kernel comment
 // for the lane mapping).
+#include <stdlib.h>
 #include "spmm_args.cuh"
 
 namespace srb {
@@ -56,7 +57,7 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmArgs& a, int row, int gl
         }
       } else {
         const uint32_t stp = a.pstep ? (uint32_t)*a.pstep : 0u;
-        const uint32_t grow = (uint32_t)(a.noise_row_base + a.row_begin + row);
+        const uint32_t grow = (uint32_t)(a.noise_row_base + (a.row_begin + row) * a.noise_row_stride);
         // counter = (row, column block | view << 16, layer tag, step): (view, step) pairs never share a stream
         const uint32_t vw = a.poff.y << 16;
         const uint4 r0 = philox4x32_10(make_uint4(grow, (uint32_t)gl | vw, a.poff.x, stp), a.pkey);
@@ -145,8 +146,24 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmArgs& a, int row, int gl
 // Each lane loads one (col, val) pair per iteration (coalesced, prefetched one iteration ahead) and
 // the pairs are walked with group-wide shuffles; every X-row gather is two 128-bit ld.global.nc per
 // lane (LPR lanes x 16 B = one contiguous half row), issued 2*SB at a time before the FMAs.
-template <int D, bool MASKED>
-__device__ __forceinline__ void spmm_gather(const SpmmArgs& a, int p, int end, int stride, int gl, float4& acc0, float4& acc1) {
+//
+// ASYNC (tables beyond L2, D >= 64): the product is then bound by how many bytes of gathers an SM keeps in flight, and
+// the LDG path is capped by the registers that receive the data (8 x 16 B per lane, ~130 KB per SM at the occupancy
+// the kernel reaches).  Every second sub-batch is therefore fetched with cp.async into a per-lane staging slot in
+// shared memory (each lane reads back exactly the 2 x 16 B it requested: no cross-lane hand-off, only
+// cp.async.wait_group), issued BEFORE the register sub-batch: twice the bytes in flight with the same registers.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+constexpr int SPMM_STAGE_F4 = 8 * 32;  // float4 slots per warp: 4 rows x 2 halves x 32 lanes (4 KB)
+
+template <int D, bool MASKED, bool ASYNC = false>
+__device__ __forceinline__ void spmm_gather(const SpmmArgs& a, int p, int end, int stride, int gl, float4& acc0, float4& acc1,
+                                            float4* stg = nullptr) {
   constexpr int LPR = D / 8;
   constexpr int HALF = D / 2;
   constexpr int SB = LPR < 4 ? LPR : 4;  // sub-batch: 2*SB independent 128-bit gathers per lane in flight
@@ -173,7 +190,43 @@ __device__ __forceinline__ void spmm_gather(const SpmmArgs& a, int p, int end, i
       vn = a.stream ? __ldcs(a.vals + p + stride + gl) : __ldg(a.vals + p + stride + gl);
       if (masked) hitn = (__ldg(a.col_mask + (cn >> 5)) >> (cn & 31)) & 1u;
     }
-    if (!masked) {
+    if (!masked && ASYNC && LPR >= 2 * SB) {
+#pragma unroll
+      for (int j0 = 0; j0 < LPR; j0 += 2 * SB) {
+        if (j0 > 0 && !__any_sync(SRB_FULL_MASK, p + j0 < end)) break;
+        float vb[SB];
+#pragma unroll
+        for (int j = 0; j < SB; ++j) {  // second sub-batch: shared-memory staging slots of this lane
+          const int cc = __shfl_sync(SRB_FULL_MASK, c, j0 + SB + j, LPR);
+          vb[j] = __shfl_sync(SRB_FULL_MASK, v, j0 + SB + j, LPR);
+          const float* xr = a.X + (size_t)cc * D + gl * 4;
+          cp_async16(stg + (2 * j) * 32, xr);
+          cp_async16(stg + (2 * j + 1) * 32, xr + HALF);
+        }
+        cp_async_commit();
+        float vv[SB];
+        float4 x0[SB], x1[SB];
+#pragma unroll
+        for (int j = 0; j < SB; ++j) {  // first sub-batch: registers
+          const int cc = __shfl_sync(SRB_FULL_MASK, c, j0 + j, LPR);
+          vv[j] = __shfl_sync(SRB_FULL_MASK, v, j0 + j, LPR);
+          const float* xr = a.X + (size_t)cc * D + gl * 4;
+          x0[j] = ldg4(xr);
+          x1[j] = ldg4(xr + HALF);
+        }
+#pragma unroll
+        for (int j = 0; j < SB; ++j) {
+          acc0 = f4_fma(vv[j], x0[j], acc0);
+          acc1 = f4_fma(vv[j], x1[j], acc1);
+        }
+        cp_async_wait_all();
+#pragma unroll
+        for (int j = 0; j < SB; ++j) {
+          acc0 = f4_fma(vb[j], stg[(2 * j) * 32], acc0);
+          acc1 = f4_fma(vb[j], stg[(2 * j + 1) * 32], acc1);
+        }
+      }
+    } else if (!masked) {
 #pragma unroll
       for (int j0 = 0; j0 < LPR; j0 += SB) {
         if (j0 > 0 && !__any_sync(SRB_FULL_MASK, p + j0 < end)) break;
@@ -244,11 +297,13 @@ __device__ __forceinline__ void xor_reduce_groups(float4& acc0, float4& acc1, in
 // A power-law graph at config-5 scale has rows with millions of non-zeros; one CTA walking such a row alone would
 // take longer than the rest of the product, so those rows are cut into chunks here and summed (in chunk order:
 // deterministic) by the main kernel.
-template <int D, bool MASKED>
+template <int D, bool MASKED, bool ASYNC>
 __global__ void __launch_bounds__(256) spmm_hub_kernel(const SpmmArgs a) {
   constexpr int LPR = D / 8;
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
+  __shared__ float4 stage[ASYNC ? 8 * SPMM_STAGE_F4 : 1];
+  float4* stg = ASYNC ? stage + wib * SPMM_STAGE_F4 + lane : nullptr;
   const int grp = lane / LPR;
   const int gl = lane % LPR;
   const int n_work = a.seg ? a.n_cta : (a.n_vlong_dev ? min(a.n_vlong_dev[4], a.n_work) : a.n_work);
@@ -270,7 +325,7 @@ __global__ void __launch_bounds__(256) spmm_hub_kernel(const SpmmArgs a) {
     const int wbeg = beg + wib * per;
     const int wend = min(end, wbeg + per);
     float4 acc0 = f4_zero(), acc1 = f4_zero();
-    spmm_gather<D, MASKED>(a, wbeg + grp * LPR, wend, 32, gl, acc0, acc1);
+    spmm_gather<D, MASKED, ASYNC>(a, wbeg + grp * LPR, wend, 32, gl, acc0, acc1, stg);
     xor_reduce_groups(acc0, acc1, LPR);
     if (grp == 0) {
       part[wib][0][gl] = acc0;
@@ -294,10 +349,12 @@ __global__ void __launch_bounds__(256) spmm_hub_kernel(const SpmmArgs a) {
 }
 
 // Short segments of the column-blocked lists: a warp each (lane groups stride the segment, like a "long" row).
-template <int D, bool MASKED>
+template <int D, bool MASKED, bool ASYNC>
 __global__ void __launch_bounds__(256) spmm_seg_warp_kernel(const SpmmArgs a) {
   constexpr int LPR = D / 8;
   const int lane = threadIdx.x & 31;
+  __shared__ float4 stage[ASYNC ? 8 * SPMM_STAGE_F4 : 1];
+  float4* stg = ASYNC ? stage + (threadIdx.x >> 5) * SPMM_STAGE_F4 + lane : nullptr;
   const int grp = lane / LPR;
   const int gl = lane % LPR;
   const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -306,7 +363,7 @@ __global__ void __launch_bounds__(256) spmm_seg_warp_kernel(const SpmmArgs a) {
     const int w = __ldg(a.order_warp + k);
     const int beg = __ldg(a.seg + 2 * w), end = __ldg(a.seg + 2 * w + 1);
     float4 acc0 = f4_zero(), acc1 = f4_zero();
-    spmm_gather<D, MASKED>(a, beg + grp * LPR, end, 32, gl, acc0, acc1);
+    spmm_gather<D, MASKED, ASYNC>(a, beg + grp * LPR, end, 32, gl, acc0, acc1, stg);
     xor_reduce_groups(acc0, acc1, LPR);
     if (grp == 0) {
       float* dst = a.hub_part + (size_t)w * D + gl * 4;
@@ -345,12 +402,14 @@ __global__ void __launch_bounds__(256) spmm_hub_finish_kernel(const SpmmArgs a) 
   }
 }
 
-template <int D, bool MASKED>
+template <int D, bool MASKED, bool ASYNC>
 __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmArgs a) {
   constexpr int LPR = D / 8;     // lanes per row
   constexpr int RPW = 32 / LPR;  // rows per warp (short rows)
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
+  __shared__ float4 stage[ASYNC ? 8 * SPMM_STAGE_F4 : 1];
+  float4* stg = ASYNC ? stage + wib * SPMM_STAGE_F4 + lane : nullptr;
   const int grp = lane / LPR;
   const int gl = lane % LPR;
   const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -381,7 +440,7 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmArgs a) {
     const int wbeg = beg + wib * per;
     const int wend = min(end, wbeg + per);
     float4 acc0 = f4_zero(), acc1 = f4_zero();
-    spmm_gather<D, MASKED>(a, wbeg + grp * LPR, wend, 32, gl, acc0, acc1);
+    spmm_gather<D, MASKED, ASYNC>(a, wbeg + grp * LPR, wend, 32, gl, acc0, acc1, stg);
     xor_reduce_groups(acc0, acc1, LPR);
     if (grp == 0) {
       part[wib][0][gl] = acc0;
@@ -416,7 +475,7 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmArgs a) {
     }
     if (is_long) p += grp * LPR;
     float4 acc0 = f4_zero(), acc1 = f4_zero();
-    spmm_gather<D, MASKED>(a, p, end, is_long ? 32 : LPR, gl, acc0, acc1);
+    spmm_gather<D, MASKED, ASYNC>(a, p, end, is_long ? 32 : LPR, gl, acc0, acc1, stg);
     if (is_long) {  // combine the lane groups; group 0 owns the row
       xor_reduce_groups(acc0, acc1, LPR);
       valid = valid && grp == 0;
@@ -444,7 +503,12 @@ __global__ void __launch_bounds__(256) reduce_rows_kernel(const SpmmArgs a, cons
   peer_wait(a.ps);  // every rank's partial rows have landed in the staging area
   for (int item = warp0; item < n_items; item += nwarps) {
     const int k = item * RPW + grp;
-    const bool valid = k < r.n_slice;
+    bool valid = k < r.n_slice;
+    if (r.mask) {  // last forward layer: only the batch's items carry a fresh partial sum (warp-uniform skip)
+      const int row = r.slice_begin + k;
+      valid = valid && ((__ldg(r.mask + (row >> 5)) >> (row & 31)) & 1u);
+      if (!__any_sync(SRB_FULL_MASK, valid)) continue;
+    }
     float4 acc0 = f4_zero(), acc1 = f4_zero();
     if (valid) {
       const float* src = r.stage + (size_t)k * D + gl * 4;
@@ -471,6 +535,47 @@ __global__ void __launch_bounds__(256) reduce_rows_kernel(const SpmmArgs a, cons
   peer_signal(a.ps);  // the finished rows are in every rank's copy
 }
 
+// The epilogue alone (identity product): one lane group per row reads X[row] and runs the common epilogue on it.
+template <int D>
+__global__ void __launch_bounds__(256) rows_epilogue_kernel(const SpmmArgs a) {
+  constexpr int LPR = D / 8;
+  constexpr int RPW = 32 / LPR;
+  constexpr int HALF = D / 2;
+  const int lane = threadIdx.x & 31;
+  const int grp = lane / LPR;
+  const int gl = lane % LPR;
+  const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int n_items = (a.n_rows + RPW - 1) / RPW;
+  for (int item = warp0; item < n_items; item += nwarps) {
+    const int row = item * RPW + grp;
+    const bool valid = row < a.n_rows;
+    float4 acc0 = f4_zero(), acc1 = f4_zero();
+    if (valid) {
+      const float* src = a.X + (size_t)row * D + gl * 4;
+      acc0 = a.stream ? __ldcs(reinterpret_cast<const float4*>(src)) : ldg4(src);
+      acc1 = a.stream ? __ldcs(reinterpret_cast<const float4*>(src + HALF)) : ldg4(src + HALF);
+    }
+    spmm_epilogue<D>(a, row, gl, acc0, acc1, valid);
+  }
+}
+
+int launch_rows_epilogue(const SpmmArgs& a, int d, cudaStream_t st) {
+  if (a.n_rows <= 0) return SRB_OK;
+  const int rpw = 32 / (d / 8);
+  long long blocks = ((long long)(a.n_rows + rpw - 1) / rpw + 7) / 8;
+  const long long cap = (long long)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  switch (d) {
+    case 32: rows_epilogue_kernel<32><<<(int)blocks, 256, 0, st>>>(a); break;
+    case 64: rows_epilogue_kernel<64><<<(int)blocks, 256, 0, st>>>(a); break;
+    case 128: rows_epilogue_kernel<128><<<(int)blocks, 256, 0, st>>>(a); break;
+    default: set_error("rows_epilogue: unsupported d=%d (32, 64, 128)", d); return SRB_ERR_ARG;
+  }
+  return post_launch("rows_epilogue_kernel");
+}
+
 int launch_reduce_rows(const SpmmArgs& a, const ReduceArgs& r, int d, cudaStream_t st) {
   if (r.n_slice <= 0) return SRB_OK;
   const int rpw = 32 / (d / 8);
@@ -487,24 +592,27 @@ int launch_reduce_rows(const SpmmArgs& a, const ReduceArgs& r, int d, cudaStream
   return post_launch("reduce_rows_kernel");
 }
 
-template <int D>
-static void launch_spmm_d(const SpmmArgs& a, int hub_blocks, int blocks, cudaStream_t st) {
-  const bool m = a.col_mask != nullptr;
+template <int D, bool M, bool AS>
+static void launch_spmm_dma(const SpmmArgs& a, int hub_blocks, int blocks, cudaStream_t st) {
   if (hub_blocks > 0) {
     if (a.seg && a.n_warp > 0) {
       const int wb = max(1, min((a.n_warp + 7) / 8, blocks));
-      if (m) spmm_seg_warp_kernel<D, true><<<wb, 256, 0, st>>>(a);
-      else spmm_seg_warp_kernel<D, false><<<wb, 256, 0, st>>>(a);
+      spmm_seg_warp_kernel<D, M, AS><<<wb, 256, 0, st>>>(a);
       g_launches.fetch_add(1, std::memory_order_relaxed);
     }
-    if (m) spmm_hub_kernel<D, true><<<hub_blocks, 256, 0, st>>>(a);
-    else spmm_hub_kernel<D, false><<<hub_blocks, 256, 0, st>>>(a);
+    spmm_hub_kernel<D, M, AS><<<hub_blocks, 256, 0, st>>>(a);
     const int nh = a.n_vlong_dev ? a.n_rows : a.n_huge;  // (device-counted lists: the capacity)
     spmm_hub_finish_kernel<D><<<max(1, min((nh + 7) / 8, hub_blocks)), 256, 0, st>>>(a);
     g_launches.fetch_add(2, std::memory_order_relaxed);
   }
-  if (m) spmm_csr_kernel<D, true><<<blocks, 256, 0, st>>>(a);
-  else spmm_csr_kernel<D, false><<<blocks, 256, 0, st>>>(a);
+  spmm_csr_kernel<D, M, AS><<<blocks, 256, 0, st>>>(a);
+}
+
+template <int D>
+static void launch_spmm_d(const SpmmArgs& a, int hub_blocks, int blocks, cudaStream_t st) {
+  if (a.col_mask != nullptr) launch_spmm_dma<D, true, false>(a, hub_blocks, blocks, st);
+  else if (D >= 64 && a.async_stage) launch_spmm_dma<D, false, (D >= 64)>(a, hub_blocks, blocks, st);
+  else launch_spmm_dma<D, false, false>(a, hub_blocks, blocks, st);
 }
 
 int launch_spmm(const SpmmArgs& a, int d, cudaStream_t st) {
@@ -527,6 +635,17 @@ int launch_spmm(const SpmmArgs& a, int d, cudaStream_t st) {
     default: set_error("spmm: unsupported d=%d (32, 64, 128)", d); return SRB_ERR_ARG;
   }
   return post_launch("spmm_csr_kernel");
+}
+
+// SRB_SPMM_ASYNC=1 stages every second gather sub-batch through cp.async + shared memory (measurement switch; results
+// are bit-identical).  Off by default: at config-5 size it measured 22.4 ms per product against 19.6 ms on the register
+// path (profiles/r02l_probe10M_*.json) -- twice the bytes in flight did not help, the LDGSTS + LDS round trip cost more.
+static bool async_stage_enabled() {
+  static const int on = [] {
+    const char* e = getenv("SRB_SPMM_ASYNC");
+    return (e && e[0] == '1') ? 1 : 0;
+  }();
+  return on != 0;
 }
 
 int fill_args(const srb_spmm_desc* d, SpmmArgs& a) {
@@ -589,10 +708,12 @@ int fill_args(const srb_spmm_desc* d, SpmmArgs& a) {
   a.world = 0;
   a.row_begin = 0;
   a.noise_row_base = 0;
+  a.noise_row_stride = 1;
   a.peer_mc = 0;
   a.ps = PeerSync{};
   // (rows + columns) x d x 4 bytes of dense operands beyond ~3/4 of the 126 MB L2: stream the one-touch data
   a.stream = ((long long)d->n_rows + d->n_cols) * d->d * 4 > (96ll << 20);
+  a.async_stage = a.stream && async_stage_enabled();  // (opt-in: measured slower, profiles/README.md r02l)
   a.stage_rank = a.stage_cap = 0;
   for (int g = 0; g < 8; ++g) a.peer[g] = a.peer_sum[g] = a.peer_p[g] = a.stage_peer[g] = nullptr;
   for (int g = 0; g < 9; ++g) a.stage_bounds[g] = 0;
@@ -605,6 +726,13 @@ extern "C" int srb_spmm_csr(const srb_spmm_desc* desc, void* stream) {
   srb::SpmmArgs a;
   SRB_TRY(srb::fill_args(desc, a));
   return srb::launch_spmm(a, desc->d, (cudaStream_t)stream);
+}
+
+extern "C" int srb_spmm_epilogue_rows(const srb_spmm_desc* desc, void* stream) {
+  srb::SpmmArgs a;
+  SRB_TRY(srb::fill_args(desc, a));
+  SRB_REQUIRE(desc->Y || desc->sum_out || desc->adam_p, "spmm_epilogue_rows: nothing to write");
+  return srb::launch_rows_epilogue(a, desc->d, (cudaStream_t)stream);
 }
 
 extern "C" int srb_spmm_csr_allgather(const srb_spmm_sharded_desc* desc, void* stream) {
@@ -656,7 +784,14 @@ extern "C" int srb_encoder_forward(const srb_encoder_desc* e, void* stream) {
   if (want_cl && !cl_hit)  // XSimGCL.py:86: default CL view is the ego embedding
     SRB_TRY(srb::check_cuda(cudaMemcpyAsync(e->cl_out, e->E0, nd * 4, cudaMemcpyDeviceToDevice, st), "encoder copy"));
   const float* x = e->E0;
-  for (int k = 0; k < L; ++k) {
+  int k0 = 0;
+  if (e->x1) {  // layer 1 was evaluated by the caller (shared by several encoders)
+    SRB_REQUIRE(L >= 2 && !e->include_ego && !(cl_hit && e->layer_cl == 1) && e->x1 != e->work0 && e->x1 != e->work1,
+                "encoder: x1 needs n_layers >= 2, include_ego == 0, layer_cl != 1 and a buffer of its own");
+    x = e->x1;
+    k0 = 1;
+  }
+  for (int k = k0; k < L; ++k) {
     srb_spmm_desc s = {};
     s.rowptr = e->rowptr;
     s.colidx = e->colidx;
@@ -681,7 +816,7 @@ extern "C" int srb_encoder_forward(const srb_encoder_desc* e, void* stream) {
     s.philox_offset = e->philox_offset + (uint64_t)k;
     s.philox_step_dev = e->philox_step_dev;
     // running sum lives in final_out; layer 1 seeds it (with E0 when the ego layer counts)
-    s.sum_in = (k == 0) ? (e->include_ego ? e->E0 : nullptr) : e->final_out;
+    s.sum_in = (k == 0) ? (e->include_ego ? e->E0 : nullptr) : ((k == 1 && e->x1) ? e->x1 : e->final_out);
     s.sum_out = e->final_out;
     s.sum_scale = last ? inv : 1.0f;
     if (last && e->last_rows && e->n_last_rows > 0 && !(cl_hit && k == e->layer_cl - 1)) {

@@ -111,8 +111,10 @@ struct SpmmArgs {
   float* peer_sum[8];  // running sum  -> every rank's buffer
   float* peer_p[8];    // updated parameters (Adam epilogue) -> every rank's copy
   int32_t stream;          // tables larger than L2: CSR arrays and outputs are touched once per product -> evict-first accesses
+  int32_t async_stage;     // with `stream`: every second gather sub-batch goes through cp.async + shared memory (more bytes in flight)
   int32_t peer_mc;         // the one peer address is an NVSwitch multicast mapping: stores go out as multimem.st
-  int32_t noise_row_base;  // Philox row id = noise_row_base + row_begin + row (global id of a row of a sharded table)
+  int32_t noise_row_base;  // Philox row id = noise_row_base + (row_begin + row) * noise_row_stride: the GLOBAL id of a row of a
+  int32_t noise_row_stride;  // sharded table (cyclic user blocks: base = rank, stride = world)
   // partial-sum push (bipartite sharding, item-side product): row r of this rank's partial product goes to the
   // staging area of the rank that owns item r: stage_peer[o] + ((size_t)stage_rank * stage_cap + r - stage_bounds[o]) * D
   float* stage_peer[8];
@@ -129,10 +131,12 @@ struct ReduceArgs {
   int32_t stage_cap;
   int32_t slice_begin;  // item id of slice row 0 (epilogue tensors are indexed by item id)
   int32_t n_slice;
+  const uint32_t* mask; // optional bitmap over item ids: only the rows whose bit is set are reduced (batch rows of the last layer)
 };
 
 int launch_spmm(const SpmmArgs& a, int d, cudaStream_t st);
 int launch_reduce_rows(const SpmmArgs& a, const ReduceArgs& r, int d, cudaStream_t st);
+int launch_rows_epilogue(const SpmmArgs& a, int d, cudaStream_t st);  // Y[r] = epilogue(X[r]), r < n_rows
 int fill_args(const srb_spmm_desc* d, SpmmArgs& a);
 
 

@@ -97,6 +97,13 @@ class TrainEngine:
         s.batch, s.params, s.adam_m, s.adam_v = ops._p(self.batch_dev), ops._p(self.params), ops._p(self.m), ops._p(self.v)
         s.step_dev, s.scalars, s.losses = ops._p(self.step_dev), ops._p(self.scalars), ops._p(self.losses)
         s.workspace, s.workspace_bytes = C.c_void_p(ws_ptr), ws_bytes
+        # this engine's own fork / join resources (BPR beside InfoNCE): two engines on one device never share events
+        self._fork_stream = torch.cuda.Stream(device=self.dev)
+        self._fork_events = (torch.cuda.Event(), torch.cuda.Event())
+        for ev in self._fork_events:
+            ev.record(self._fork_stream)  # torch creates the CUDA event lazily, on first record
+        s.fork_stream = C.c_void_p(self._fork_stream.cuda_stream)
+        s.fork_event, s.join_event = (C.c_void_p(ev.cuda_event) for ev in self._fork_events)
         self.desc = s
         self.eps, self.layer_cl = float(eps), int(layer_cl)
         self.sampler = None

@@ -258,7 +258,8 @@ class SparseAdj:
         return g
 
 
-def _spmm_raw(adj, x, y=None, **epi):
+def _spmm_raw(adj, x, y=None, _entry="srb_spmm_csr", **epi):
+    """Y = epilogue(A @ X) (srb_spmm_csr); _entry="srb_spmm_epilogue_rows": the epilogue alone on the rows of X."""
     lib = _lib.require_device()
     if adj.rowptr is None:
         adj.cuda(x.device)
@@ -285,7 +286,7 @@ def _spmm_raw(adj, x, y=None, **epi):
             setattr(desc, k, _p(v))
         else:
             setattr(desc, k, v)
-    _lib.check(lib.srb_spmm_csr(C.byref(desc), _stream()), "srb_spmm_csr")
+    _lib.check(getattr(lib, _entry)(C.byref(desc), _stream()), _entry)
 
 
 class _SpmmFn(torch.autograd.Function):

@@ -36,7 +36,7 @@ def sharded_vs_single(model, data, d, L, B, batches, *, steps=3, lr=1e-3, reg=1e
     # per-rank partial sums, a different order than the single-GPU row sum).
     out = dict(loss_rel=0.0, user_rel=0.0, item_rel=0.0, m_user_rel=0.0, m_item_rel=0.0, v_user_rel=0.0, v_item_rel=0.0, upd_off_frac=0.0,
                m_rows_off_frac=0.0)
-    lo, hi = sh.user_lo, sh.user_hi
+    uid = sh.user_ids  # global ids of this rank's users (cyclic assignment)
     ilo, ihi = int(sh.ib[sh.rank]), int(sh.ib[sh.rank + 1])  # the item slice whose moments this rank owns
     for k in range(steps):
         w = batches[k % len(batches)]
@@ -48,21 +48,21 @@ def sharded_vs_single(model, data, d, L, B, batches, *, steps=3, lr=1e-3, reg=1e
         torch.cuda.synchronize()
         la, lb = sh.losses, ref.losses
         out["loss_rel"] = max(out["loss_rel"], float(((la - lb).abs() / lb.abs().clamp_min(1e-12)).max().item()))
-        out["user_rel"] = max(out["user_rel"], max_rel(sh.user_emb, ref.params[lo:hi]))
+        out["user_rel"] = max(out["user_rel"], max_rel(sh.user_emb, ref.params[uid]))
         out["item_rel"] = max(out["item_rel"], max_rel(sh.item_emb, ref.params[U:]))
-        out["m_user_rel"] = max(out["m_user_rel"], max_rel(sh.mu, ref.m[lo:hi]))
+        out["m_user_rel"] = max(out["m_user_rel"], max_rel(sh.mu, ref.m[uid]))
         out["m_item_rel"] = max(out["m_item_rel"], max_rel(sh.mi[ilo:ihi], ref.m[U + ilo:U + ihi]))
         # rows whose first moment is off by more than 1e-4 of the largest entry.  With eps > 0 a few are expected:
         # the perturbation is sign(y) * noise * eps (XSimGCL.py:90-91), and an element y that is within fp32 rounding
         # of zero takes the opposite sign under a different summation order (~1e-7 of the elements, i.e. a handful
         # per step at yelp2018 size); the flipped rows and their graph neighbours then differ by ~1 %
         off = 0
-        for a_, b_ in ((sh.mu, ref.m[lo:hi]), (sh.mi[ilo:ihi], ref.m[U + ilo:U + ihi])):
+        for a_, b_ in ((sh.mu, ref.m[uid]), (sh.mi[ilo:ihi], ref.m[U + ilo:U + ihi])):
             off += int(((a_ - b_).abs().max(1).values > 1e-4 * float(b_.abs().max().item())).sum().item())
         out["m_rows_off_frac"] = max(out["m_rows_off_frac"], off / float(sh.Ug + (ihi - ilo)))
-        out["v_user_rel"] = max(out["v_user_rel"], max_rel(sh.vu, ref.v[lo:hi]))
+        out["v_user_rel"] = max(out["v_user_rel"], max_rel(sh.vu, ref.v[uid]))
         out["v_item_rel"] = max(out["v_item_rel"], max_rel(sh.vi[ilo:ihi], ref.v[U + ilo:U + ihi]))
-        du = (sh.user_emb - pu0) - (ref.params[lo:hi] - pr0[lo:hi])
+        du = (sh.user_emb - pu0) - (ref.params[uid] - pr0[uid])
         di = (sh.item_emb - pi0) - (ref.params[U:] - pr0[U:])
         off = float(((du.abs() > 0.05 * lr).sum() + (di.abs() > 0.05 * lr).sum()).item()) / float(du.numel() + di.numel())
         out["upd_off_frac"] = max(out["upd_off_frac"], off)
@@ -70,7 +70,7 @@ def sharded_vs_single(model, data, d, L, B, batches, *, steps=3, lr=1e-3, reg=1e
     fu, fi = sh.forward_clean()
     ru, ri = ref.forward_clean()
     torch.cuda.synchronize()
-    out["final_user_rel"] = max_rel(fu, ru[lo:hi])
+    out["final_user_rel"] = max_rel(fu, ru[uid])
     out["final_item_rel"] = max_rel(fi, ri)
     sh.check_peers()
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:

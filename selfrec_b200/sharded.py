@@ -1,13 +1,18 @@
 """Bipartite-sharded multi-GPU path: one process per GPU.
 
-The normalised adjacency is A = [[0, R], [R^T, 0]].  Rank g owns a contiguous, nnz-balanced block of USERS (their
-rows of every [U, d] table never leave the GPU); the ITEM tables are replicated.  Per propagation layer only the
-item half crosses NVLink: every rank's partial product R_g^T X_u is stored by the SpMM epilogue into the staging
-area of the rank owning that item slice, the owner adds the partials, applies the epilogue and stores the finished
-rows into every rank's copy (selfrec_b200/csrc/sharded.cu).  torch.distributed is plumbing only: rendezvous of the
-symmetric-memory region (peer pointers, multicast mapping); no NCCL collective touches the data path.
+The normalised adjacency is A = [[0, R], [R^T, 0]].  Rank g owns the USERS u with u % world == g (local row
+u // world; their rows of every [U, d] table never leave the GPU); the ITEM tables are replicated.  Per propagation
+layer only the item half crosses NVLink: every rank's partial product R_g^T X_u is stored by the SpMM epilogue into the
+staging area of the rank owning that item slice, the owner adds the partials, applies the epilogue and stores the
+finished rows into every rank's copy (selfrec_b200/csrc/sharded.cu).  torch.distributed is plumbing only: rendezvous
+of the symmetric-memory region (peer pointers, multicast mapping); no NCCL collective touches the data path.
 
-Host logic here (user partition, block extraction) is plain tensor code that also runs on CPU tensors and is
+Why cyclic and not contiguous nnz-balanced blocks: ids follow first appearance in the training file
+(ui_graph.py:29-40), so on a power-law graph the hubs have the low ids -- at config-5 size an nnz-balanced 2-way split
+is 142 k users against 9.86 M, and the second rank's products (cold gathers, 70x the rows to write) take 1.5x longer.
+Every rank taking each world-th user gets the same mix of degrees, rows and non-zeros.
+
+Host logic here (user assignment, block extraction) is plain tensor code that also runs on CPU tensors and is
 exercised with a world-size-2 gloo group in tests/test_sharding_cpu.py.
 """
 import ctypes as C
@@ -18,29 +23,14 @@ import numpy as np
 from . import _lib
 
 
-def partition_rows(rowptr, world):
-    """Contiguous row blocks with (nearly) equal non-zero counts: bounds[g] .. bounds[g+1]."""
-    rowptr = np.asarray(rowptr, dtype=np.int64)
-    n = len(rowptr) - 1
-    nnz = int(rowptr[-1])
-    targets = (np.arange(1, world) * nnz) // world
-    cuts = np.searchsorted(rowptr, targets, side="left")
-    bounds = np.concatenate([[0], np.clip(cuts, 0, n), [n]]).astype(np.int64)
-    return np.maximum.accumulate(bounds)
+def local_user_count(n_users, rank, world):
+    """Users rank, rank + world, rank + 2 world, ... below n_users."""
+    return (int(n_users) - int(rank) + int(world) - 1) // int(world)
 
 
-def partition_users(user_rowptr, world, align=32):
-    """User blocks with (nearly) equal non-zero counts; inner bounds are multiples of `align` (the bitmap of a
-    block's users must start on a word) and every rank owns at least `align` users."""
-    rp = np.asarray(user_rowptr, dtype=np.int64)
-    U = len(rp) - 1
-    if U < world * align:
-        raise _lib.SrbError(f"{U} users cannot be split over {world} ranks in blocks of >= {align}")
-    b = partition_rows(rp, world)
-    b[1:-1] = (b[1:-1] + align // 2) // align * align
-    for g in range(1, world):  # keep the blocks non-empty after rounding
-        b[g] = min(max(b[g], b[g - 1] + align), (U - (world - g) * align) // align * align)
-    return b
+def user_ids_of(n_users, rank, world):
+    """Global ids of rank's users in local-row order (numpy int64)."""
+    return np.arange(int(rank), int(n_users), int(world), dtype=np.int64)
 
 
 def item_bounds(n_items, world):
@@ -48,22 +38,38 @@ def item_bounds(n_items, world):
     return np.array([g * n_items // world for g in range(world + 1)], dtype=np.int64)
 
 
-def extract_blocks(rowptr, colidx, vals, n_users, n_items, ub, ub_end):
-    """Rank-local blocks of the normalised (U+I)^2 adjacency given as CSR tensors (any device):
-    Ru [Ug x I] = A[ub:ub_end, U:] (columns: item ids) and Rt [I x Ug] = A[U:, ub:ub_end] (columns: local user
-    ids).  Returns two (rowptr, colidx, vals) triples of int32 / int32 / fp32 tensors."""
+def extract_blocks(rowptr, colidx, vals, n_users, n_items, rank, world):
+    """Rank-local blocks of the normalised (U+I)^2 adjacency given as CSR tensors (any device), for the cyclic user
+    assignment: Ru [Ug x I] = rows rank, rank + world, ... of A[:U, U:] (columns: item ids) and Rt [I x Ug] = the
+    columns of A[U:, :U] with col % world == rank, renumbered col // world (monotone: the rows stay sorted).
+    Returns two (rowptr, colidx, vals) triples of int32 / int32 / fp32 tensors."""
     import torch
-    U, I = int(n_users), int(n_items)
+    U, I, G, g = int(n_users), int(n_items), int(world), int(rank)
     rp = rowptr.to(torch.int64)
-    lo, hi = int(rp[ub]), int(rp[ub_end])
-    ru = ((rp[ub:ub_end + 1] - lo).to(torch.int32), (colidx[lo:hi] - U).to(torch.int32).contiguous(), vals[lo:hi].contiguous())
+    dev = rp.device
+    if G == 1:
+        lo, hi = 0, int(rp[U])
+        ru = (rp[:U + 1].to(torch.int32), (colidx[lo:hi] - U).to(torch.int32).contiguous(), vals[lo:hi].contiguous())
+    else:
+        rows = torch.arange(g, U, G, device=dev)
+        beg = rp[rows]
+        deg = rp[rows + 1] - beg
+        ru_ptr = torch.zeros(rows.numel() + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(deg, 0, out=ru_ptr[1:])
+        total = int(ru_ptr[-1])
+        pos = torch.arange(total, device=dev) + torch.repeat_interleave(beg - ru_ptr[:-1], deg, output_size=total)
+        ru = (ru_ptr.to(torch.int32), (colidx[pos] - U).to(torch.int32).contiguous(), vals[pos].contiguous())
+        del pos, beg, deg, rows
     ilo, ihi = int(rp[U]), int(rp[U + I])
     cols = colidx[ilo:ihi]
-    keep = (cols >= ub) & (cols < ub_end)
-    pref = torch.zeros(ihi - ilo + 1, dtype=torch.int64, device=cols.device)
+    if G == 1:
+        rt = ((rp[U:U + I + 1] - ilo).to(torch.int32), cols.to(torch.int32).contiguous(), vals[ilo:ihi].contiguous())
+        return ru, rt
+    keep = (cols % G) == g
+    pref = torch.zeros(ihi - ilo + 1, dtype=torch.int64, device=dev)
     torch.cumsum(keep, 0, out=pref[1:])
     rt_ptr = pref[rp[U:U + I + 1] - ilo].to(torch.int32)
-    rt = (rt_ptr, (cols[keep] - ub).to(torch.int32).contiguous(), vals[ilo:ihi][keep].contiguous())
+    rt = (rt_ptr, torch.div(cols[keep], G, rounding_mode="floor").to(torch.int32).contiguous(), vals[ilo:ihi][keep].contiguous())
     return ru, rt
 
 
@@ -71,8 +77,8 @@ class ShardedEngine:
     """LightGCN / SimGCL / XSimGCL training on bipartite-sharded tables; world == 1 works without torch.distributed.
 
     Same constructor surface as TrainEngine.  Every rank must feed the SAME batch buffer to step().  Parameters:
-    `user_emb` = this rank's user block [Ug, d] (users user_lo .. user_hi), `item_emb` = the full replicated
-    [I, d] item table.  The in-kernel Philox noise is keyed by global row ids, so a sharded run with the same
+    `user_emb` = this rank's users [Ug, d] (global ids `user_ids`: rank, rank + world, ...), `item_emb` = the full
+    replicated [I, d] item table.  The in-kernel Philox noise is keyed by global row ids, so a sharded run with the same
     philox_seed draws the noise the single-GPU TrainEngine draws."""
 
     def __init__(self, model, data, emb_size, n_layers, batch_size, lr, reg, *, eps=0.0, tau=0.2, cl_rate=0.0, layer_cl=0,
@@ -105,10 +111,11 @@ class ShardedEngine:
         adj = na if isinstance(na, ops.SparseAdj) else ops.SparseAdj(na)
         had = adj.rowptr is not None
         adj.cuda(dev)
-        self.bounds = partition_users(adj.rowptr[: self.U + 1].cpu().numpy(), self.world)
-        self.user_lo, self.user_hi = int(self.bounds[self.rank]), int(self.bounds[self.rank + 1])
-        self.Ug = self.user_hi - self.user_lo
-        ru, rt = extract_blocks(adj.rowptr, adj.colidx, adj.vals, self.U, self.I, self.user_lo, self.user_hi)
+        if self.U < self.world:
+            raise _lib.SrbError(f"{self.U} users cannot be spread over {self.world} ranks")
+        self.Ug = local_user_count(self.U, self.rank, self.world)
+        self.user_ids = torch.arange(self.rank, self.U, self.world, device=dev)  # global id of every local row
+        ru, rt = extract_blocks(adj.rowptr, adj.colidx, adj.vals, self.U, self.I, self.rank, self.world)
         self.Ru = ops.SparseAdj.from_device(*ru, (self.Ug, self.I), symmetric=False)
         self.Rt = ops.SparseAdj.from_device(*rt, (self.I, self.Ug), symmetric=False)
         self.nnzA = adj.nnz
@@ -117,7 +124,9 @@ class ShardedEngine:
         self.ib = item_bounds(self.I, self.world)
         # ---- memory ----
         lay = _lib.ShardLayout()
-        _lib.check(lib.srb_shard_plan(self.U, self.I, self.Ug, self.d, self.B, self.world, C.byref(lay)), "srb_shard_plan")
+        gu, gt = self.Ru.graph_struct(self.d), self.Rt.graph_struct(self.d)
+        _lib.check(lib.srb_shard_plan(self.U, self.I, self.Ug, self.d, self.B, self.world, int(gu.hub.n_work), int(gt.hub.n_work),
+                                      C.byref(lay)), "srb_shard_plan")
         self.layout = lay
         self.sym_handle = None
         mc_ptr = 0
@@ -150,16 +159,17 @@ class ShardedEngine:
                 for lo in range(0, self.U, chunk):  # the same stream on every rank; keep the owned rows
                     hi = min(self.U, lo + chunk)
                     blk = torch.empty((hi - lo, self.d), device=dev).uniform_(-bound_u, bound_u, generator=g)
-                    a, b = max(lo, self.user_lo), min(hi, self.user_hi)
-                    if a < b:
-                        self.user_emb[a - self.user_lo: b - self.user_lo].copy_(blk[a - lo: b - lo])
+                    first = lo + (self.rank - lo) % self.world  # first owned id >= lo
+                    if first < hi:
+                        mine = blk[first - lo:: self.world]
+                        self.user_emb[first // self.world: first // self.world + mine.shape[0]].copy_(mine)
                 self.item_emb.uniform_(-bound_i, bound_i, generator=g)
             else:
                 g = torch.Generator().manual_seed(int(philox_seed) & 0x7FFFFFFF)  # every rank starts from the same tables
                 init_user = torch.nn.init.xavier_uniform_(torch.empty(self.U, self.d), generator=g)
                 init_item = torch.nn.init.xavier_uniform_(torch.empty(self.I, self.d), generator=g)
         if init_user is not None:
-            self.user_emb.copy_(torch.as_tensor(init_user)[self.user_lo: self.user_hi])
+            self.user_emb.copy_(torch.as_tensor(init_user)[self.rank:: self.world])
             self.item_emb.copy_(torch.as_tensor(init_item))
         self.mu, self.vu = torch.zeros_like(self.user_emb), torch.zeros_like(self.user_emb)
         self.mi = torch.zeros((self.I, self.d), device=dev)
@@ -176,9 +186,7 @@ class ShardedEngine:
         s.lr, s.beta1, s.beta2, s.adam_eps, s.l2_div = float(lr), 0.9, 0.999, 1e-8, float(l2_div)
         s.noise_mode = 2 if model in ("SimGCL", "XSimGCL") else 0
         s.philox_seed = int(philox_seed)
-        for g in range(self.world + 1):
-            s.user_bounds[g] = int(self.bounds[g])
-        s.Ru, s.Rt = self.Ru.graph_struct(self.d), self.Rt.graph_struct(self.d)
+        s.Ru, s.Rt = gu, gt
         p = ops._p
         s.batch, s.pu, s.mu, s.vu, s.mi, s.vi = p(self.batch_dev), p(self.user_emb), p(self.mu), p(self.vu), p(self.mi), p(self.vi)
         s.step_dev, s.scalars, s.losses = p(self.step_dev), p(self.scalars), p(self.losses)
@@ -271,9 +279,12 @@ class ShardedEngine:
         torch = self.torch
         if self.world == 1:
             return local.clone()
-        sizes = [int(self.bounds[g + 1] - self.bounds[g]) for g in range(self.world)]
+        sizes = [local_user_count(self.U, g, self.world) for g in range(self.world)]
         pad = torch.zeros((max(sizes), self.d), device=self.dev)
         pad[: self.Ug].copy_(local)
         outs = [torch.empty_like(pad) for _ in range(self.world)]
         self.dist.all_gather(outs, pad, group=self.group)
-        return torch.cat([o[:n] for o, n in zip(outs, sizes)], 0)
+        full = torch.empty((self.U, self.d), device=self.dev)
+        for g, (o, n) in enumerate(zip(outs, sizes)):
+            full[g:: self.world].copy_(o[:n])
+        return full

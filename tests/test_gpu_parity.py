@@ -149,6 +149,31 @@ def test_philox_noise_statistics(torch_cuda, tiny):
     assert 0.09 < u.mean() < 0.12  # E[u]/sqrt(64 E[u^2]) = 0.5 / sqrt(64/3) = 0.108
 
 
+def test_epilogue_rows_equals_identity_product(torch_cuda):
+    """srb_spmm_epilogue_rows (the noise SimGCL's perturbed encoders add to the shared first product, SimGCL.py:87-88)
+    is the SpMM with the identity matrix: same Philox stream / noise tensor, same running sum -- bit for bit."""
+    torch = torch_cuda
+    import scipy.sparse as sp
+    from selfrec_b200 import ops
+    rng = np.random.default_rng(11)
+    n = 1000
+    eye = ops.SparseAdj(sp.identity(n, dtype=np.float32, format="csr")).cuda()
+    for d in (32, 64, 128):
+        x = torch.from_numpy(rng.standard_normal((n, d)).astype(np.float32)).cuda()
+        noise = torch.from_numpy(rng.random((n, d), dtype=np.float32)).cuda()
+        base = torch.from_numpy(rng.standard_normal((n, d)).astype(np.float32)).cuda()
+        step = torch.tensor([7], dtype=torch.int32, device="cuda")
+        for epi in (dict(noise_mode=2, eps=0.1, philox_seed=99, philox_offset=(1 << 32) | 0x10, philox_step_dev=step),
+                    dict(noise_mode=1, noise=noise, eps=0.2)):
+            outs = []
+            for entry in ("srb_spmm_csr", "srb_spmm_epilogue_rows"):
+                y, sm = torch.empty_like(x), torch.empty_like(x)
+                ops._spmm_raw(eye, x, y, _entry=entry, sum_in=base, sum_out=sm, sum_scale=0.5, **epi)
+                outs.append((y.cpu().numpy(), sm.cpu().numpy()))
+            assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+            assert not np.array_equal(outs[1][0], x.cpu().numpy())
+
+
 # ------------------------------------------------------------------------------------------
 # (ii)(iii) losses, op-level drop-in
 # ------------------------------------------------------------------------------------------

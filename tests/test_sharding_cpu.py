@@ -1,4 +1,4 @@
-"""Bipartite-sharding host logic on CPU, incl. a real world-size-2 gloo process group: user partition, per-rank
+"""Bipartite-sharding host logic on CPU, incl. a real world-size-2 gloo process group: cyclic user assignment, per-rank
 blocks Ru / Rt, and the layer exchange (partial item products summed over ranks) reproduce the unsharded product."""
 import os
 import sys
@@ -23,53 +23,50 @@ def _bipartite(n_users, n_items, nnz, seed):
     return R.tocsr(), A
 
 
-def test_partition_rows_and_users():
-    from selfrec_b200.sharded import item_bounds, partition_rows, partition_users
+def test_cyclic_user_assignment():
+    from selfrec_b200.sharded import item_bounds, local_user_count, user_ids_of
+    for U in (1, 7, 64, 1001):
+        for world in (1, 2, 3, 8):
+            if U < world:
+                continue
+            ids = [user_ids_of(U, g, world) for g in range(world)]
+            assert [len(x) for x in ids] == [local_user_count(U, g, world) for g in range(world)]
+            allu = np.sort(np.concatenate(ids))
+            assert np.array_equal(allu, np.arange(U))                      # every user exactly once
+            for g, x in enumerate(ids):
+                assert (x % world == g).all() and np.array_equal(x // world, np.arange(len(x)))  # local row = id // world
+            ib = item_bounds(1001, world)
+            assert ib[0] == 0 and ib[-1] == 1001 and (np.diff(ib) > 0).all() and np.diff(ib).max() <= -(-1001 // world)
+    # hubs at the low ids (first-appearance ids of a power-law file): the cyclic split balances non-zeros AND rows
     rng = np.random.default_rng(0)
-    deg = np.concatenate([rng.zipf(1.5, 500) % 300, np.zeros(20, int), [4000]])  # hubs, empty rows, one giant row
-    rowptr = np.concatenate([[0], np.cumsum(deg)])
-    for world in (1, 2, 3, 8):
-        b = partition_rows(rowptr, world)
-        assert b[0] == 0 and b[-1] == len(deg) and (np.diff(b) >= 0).all() and len(b) == world + 1
-        per = np.diff(rowptr[b])
-        assert per.sum() == rowptr[-1]
-        assert per.max() <= rowptr[-1] / world + deg.max()  # at most one row over the ideal share
-        bu = partition_users(rowptr, world)
-        assert bu[0] == 0 and bu[-1] == len(deg) and (np.diff(bu) >= 32).all()
-        assert all(x % 32 == 0 for x in bu[1:-1])
-        ib = item_bounds(1001, world)
-        assert ib[0] == 0 and ib[-1] == 1001 and (np.diff(ib) > 0).all() and np.diff(ib).max() <= -(-1001 // world)
-    # a giant first row must not starve the other ranks
-    bu = partition_users(np.concatenate([[0], np.cumsum([10**6] + [1] * 511)]), 8)
-    assert (np.diff(bu) >= 32).all()
-    with pytest.raises(Exception):
-        partition_users(np.arange(41), 2)  # 40 users cannot give two blocks of >= 32
+    deg = np.sort(rng.zipf(1.3, 100000) % 50000)[::-1]
+    for world in (2, 4, 8):
+        per = np.array([deg[g::world].sum() for g in range(world)], dtype=np.float64)
+        assert per.max() / per.mean() < 1.25
 
 
 def test_extract_blocks_tile_the_adjacency():
     import torch
-    from selfrec_b200.sharded import extract_blocks, partition_users
-    U, I = 400, 150
+    from selfrec_b200.sharded import extract_blocks, local_user_count
+    U, I = 403, 150
     R, A = _bipartite(U, I, 6000, 1)
     rp, ci, vv = (torch.from_numpy(np.asarray(x)) for x in (A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data))
     for world in (1, 2, 4):
-        b = partition_users(A.indptr[:U + 1], world)
-        rus, rts = [], []
         for g in range(world):
-            (p1, c1, v1), (p2, c2, v2) = extract_blocks(rp, ci, vv, U, I, int(b[g]), int(b[g + 1]))
-            ug = int(b[g + 1] - b[g])
-            rus.append(sp.csr_matrix((v1.numpy(), c1.numpy(), p1.numpy()), shape=(ug, I)))
-            rts.append(sp.csr_matrix((v2.numpy(), c2.numpy(), p2.numpy()), shape=(I, ug)))
-            assert rts[-1].has_sorted_indices and rus[-1].has_sorted_indices
-        assert abs(sp.vstack(rus) - R).max() == 0
-        assert abs(sp.hstack(rts) - R.T).max() == 0
+            (p1, c1, v1), (p2, c2, v2) = extract_blocks(rp, ci, vv, U, I, g, world)
+            ug = local_user_count(U, g, world)
+            ru = sp.csr_matrix((v1.numpy(), c1.numpy(), p1.numpy()), shape=(ug, I))
+            rt = sp.csr_matrix((v2.numpy(), c2.numpy(), p2.numpy()), shape=(I, ug))
+            assert ru.has_sorted_indices and rt.has_sorted_indices
+            assert abs(ru - R[g::world]).max() == 0            # rows g, g + world, ... of R
+            assert abs(rt - R.T.tocsr()[:, g::world]).max() == 0  # the matching columns of R^T, renumbered id // world
 
 
 def _worker(rank, world, port, ret):
     import torch
     import torch.distributed as dist
     sys.path.insert(0, ROOT)
-    from selfrec_b200.sharded import extract_blocks, item_bounds, partition_users
+    from selfrec_b200.sharded import extract_blocks, item_bounds, local_user_count
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     U, I, d = 400, 150, 32
@@ -77,13 +74,12 @@ def _worker(rank, world, port, ret):
     rng = np.random.default_rng(5)
     X = rng.standard_normal((U + I, d)).astype(np.float32)
     rp, ci, vv = (torch.from_numpy(np.asarray(x)) for x in (A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data))
-    b = partition_users(A.indptr[:U + 1], world)
-    lo, hi = int(b[rank]), int(b[rank + 1])
-    (p1, c1, v1), (p2, c2, v2) = extract_blocks(rp, ci, vv, U, I, lo, hi)
-    Ru = sp.csr_matrix((v1.numpy(), c1.numpy(), p1.numpy()), shape=(hi - lo, I))
-    Rt = sp.csr_matrix((v2.numpy(), c2.numpy(), p2.numpy()), shape=(I, hi - lo))
+    ug = local_user_count(U, rank, world)
+    (p1, c1, v1), (p2, c2, v2) = extract_blocks(rp, ci, vv, U, I, rank, world)
+    Ru = sp.csr_matrix((v1.numpy(), c1.numpy(), p1.numpy()), shape=(ug, I))
+    Rt = sp.csr_matrix((v2.numpy(), c2.numpy(), p2.numpy()), shape=(I, ug))
     ib = item_bounds(I, world)
-    xu, xi = X[lo:hi], X[U:]
+    xu, xi = X[:U][rank::world], X[U:]   # this rank's users: rank, rank + world, ...
     for _ in range(2):  # two propagation layers
         part = torch.from_numpy((Rt @ xu).astype(np.float32))  # this rank's partial item product
         yu = (Ru @ xi).astype(np.float32)                      # local user half
@@ -100,7 +96,7 @@ def _worker(rank, world, port, ret):
         xi = torch.cat([o[:n] for o, n in zip(outs, sizes)]).numpy()
         xu = yu
     ref = A @ (A @ X)
-    ok = np.allclose(xu, ref[lo:hi], rtol=1e-5, atol=1e-5) and np.allclose(xi, ref[U:], rtol=1e-5, atol=1e-5)
+    ok = np.allclose(xu, ref[:U][rank::world], rtol=1e-5, atol=1e-5) and np.allclose(xi, ref[U:], rtol=1e-5, atol=1e-5)
     out = torch.tensor([1.0 if ok else 0.0])
     dist.all_reduce(out, op=dist.ReduceOp.MIN)
     if rank == 0:
