@@ -441,7 +441,10 @@ def record_config5(args, dev, world, rank, dist):
         rec["spmm"] = {"kernel": "spmm_hub_kernel<128> + spmm_csr_kernel<128>", "ms_per_launch": sp_ms, "algorithmic_bytes": alg,
                        "achieved_gbs": alg / sp_ms / 1e6, "frac_of_hbm": alg / sp_ms / 1e6 / pk["hbm_gbs"],
                        "gather_bytes": 4 * nnzA * d, "gather_gbs": 4 * nnzA * d / sp_ms / 1e6, "dram_traffic": traffic,
-                       "traffic_source": TRAFFIC_FILE if traffic else None}
+                       "traffic_source": TRAFFIC_FILE if traffic else None,
+                       # what the memory system actually moves: on a graph without community structure every non-zero whose
+                       # column is not among the ~200 k rows L2 can hold costs a 512-byte DRAM read
+                       "dram_frac_of_hbm": (traffic / sp_ms / 1e6 / pk["hbm_gbs"]) if traffic else None}
         torch.manual_seed(5)
         eng = TrainEngine("SimGCL", data, d, L, B, 1e-3, 1e-4, device=dev, philox_seed=55, **kw)
         g = eng.capture()

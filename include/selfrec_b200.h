@@ -584,8 +584,10 @@ int srb_spmm_csr_allgather(const srb_spmm_sharded_desc* desc, void* stream);
  * -- their rows of every [U, d] table stay on that GPU -- and the item tables are replicated; per propagation layer only the item half is exchanged: each rank's partial
  * product R_g^T X_u is stored by the SpMM epilogue into the staging area of the rank that owns the item slice
  * (P2P stores, reduce-scatter), the owner adds the partials in rank order, applies the epilogue and stores the
- * finished rows into every rank's copy (all-gather; one multicast store per row when sym_mc is given).  Item slice
- * of rank g: [g * I / world, (g+1) * I / world).
+ * finished rows into every rank's copy (all-gather; one multicast store per row when sym_mc is given).  With sym_mc the
+ * reduce-scatter goes through the NVSwitch instead (NVLS): partial products stay in the rank's own copy of the
+ * staging buffer and the owner reads their sum with multimem.ld_reduce -- one reduced row of ingress instead of
+ * world - 1 partial rows.  Item slice of rank g: [g * I / world, (g+1) * I / world).
  *   Ru  CSR [n_local_users x n_items]: rows = this rank's users (local rows), columns = item ids
  *   Rt  CSR [n_items x n_local_users]: its transpose (columns = local user ids); values = the rank's block of the
  *       normalised adjacency (data/graph.py:10-24)
@@ -621,6 +623,12 @@ typedef struct srb_shard_desc {
   int64_t sym_bytes;
   void* workspace;
   int64_t workspace_bytes;
+  /* optional (all three or none): a cudaStream_t and two cudaEvent_t (timing disabled) of the caller.  With them the
+   * owner-side reduction of a layer (NVLink-bound) runs on fork_stream beside the user-side product (local compute). */
+  void* fork_stream;
+  void* fork_event;
+  void* join_event;
+  int32_t nvls; /* != 0 (needs sym_mc): reduce-scatter through the NVSwitch (multimem.ld_reduce) instead of P2P partial pushes */
 } srb_shard_desc;
 
 typedef struct srb_shard_layout {

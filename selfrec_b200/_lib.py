@@ -128,7 +128,8 @@ class ShardDesc(C.Structure):
         ("noise_mode", C.c_int32), ("philox_seed", C.c_uint64),
         ("Ru", GraphCsr), ("Rt", GraphCsr), ("batch", VP), ("pu", VP), ("mu", VP), ("vu", VP), ("mi", VP), ("vi", VP),
         ("step_dev", VP), ("scalars", VP), ("losses", VP), ("sym", VP * 8), ("sym_mc", VP), ("sym_bytes", C.c_int64),
-        ("workspace", VP), ("workspace_bytes", C.c_int64),
+        ("workspace", VP), ("workspace_bytes", C.c_int64), ("fork_stream", VP), ("fork_event", VP), ("join_event", VP),
+        ("nvls", C.c_int32),
     ]
 
 

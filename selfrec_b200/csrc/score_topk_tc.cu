@@ -329,18 +329,65 @@ __global__ void __launch_bounds__(256) tc_rescore_kernel(const RescoreArgs a) {
   const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (q >= a.n_q) return;
   const int cnt_a = a.cand_n[(size_t)q * 2], cnt_b = a.cand_n[(size_t)q * 2 + 1];
-  const int cnt = cnt_a + cnt_b;
-  // 48 candidate slots (24 per column half) on 32 lanes: lane l owns slots l and l + 32
+  const int K = a.k;
+  const float bmax = __uint_as_float(*a.bmax_bits);
+  const float E = (1.0f / 512.0f + 1.0f / 65536.0f + 1.0f / 262144.0f) * a.unorm[q] * bmax;  // TF32 truncation + slot tags
+  // ---- prune by approximate score before any exact work ----
+  // Every exact score lies within E of its approximate score.  Let a_K be the K-th largest approximate score of the
+  // candidates: K candidates have an exact score >= a_K - E, so one whose approximate score is below a_K - 2E is beaten
+  // by at least K others and can never end in the top-K, whatever the insertion order.  Typically half of the 48 go,
+  // the survivors fit one lane each, and the second exact pass and half of the sequential insertions disappear.
+  __shared__ int32_t surv[8][TC_CAND];
+  int32_t* sv = surv[threadIdx.x >> 5];
+  int cnt;
+  {
+    float ap[2];
+    int cid[2];
+    bool have[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = lane + 32 * h;
+      have[h] = c < TC_CAND && (c % TC_LIST) < ((c < TC_LIST) ? cnt_a : cnt_b);
+      ap[h] = have[h] ? a.cand_s[(size_t)q * TC_CAND + c] : -INFINITY;
+      cid[h] = have[h] ? a.cand_i[(size_t)q * TC_CAND + c] : 0x7fffffff;
+    }
+    float cut = -INFINITY;
+    if (cnt_a + cnt_b > K) {
+      // descending rank of my approximate scores (ties broken by slot), then the value of rank K-1
+      int rk[2] = {0, 0};
+#pragma unroll 8
+      for (int l = 0; l < 32; ++l) {
+        const float o0 = __shfl_sync(SRB_FULL_MASK, ap[0], l);
+        const float o1 = __shfl_sync(SRB_FULL_MASK, ap[1], l);
+        rk[0] += (o0 > ap[0] || (o0 == ap[0] && l < lane)) + (o1 > ap[0]);
+        rk[1] += (o0 > ap[1] || o0 == ap[1]) + (o1 > ap[1] || (o1 == ap[1] && l < lane));
+      }
+      const unsigned b0 = __ballot_sync(SRB_FULL_MASK, have[0] && rk[0] == K - 1);
+      const unsigned b1 = __ballot_sync(SRB_FULL_MASK, have[1] && rk[1] == K - 1);
+      const float ak = b0 ? __shfl_sync(SRB_FULL_MASK, ap[0], __ffs(b0) - 1) : __shfl_sync(SRB_FULL_MASK, ap[1], b1 ? __ffs(b1) - 1 : 0);
+      if (b0 | b1) cut = ak - 2.0f * E;
+    }
+    const unsigned k0 = __ballot_sync(SRB_FULL_MASK, have[0] && ap[0] >= cut);
+    const unsigned k1 = __ballot_sync(SRB_FULL_MASK, have[1] && ap[1] >= cut);
+    const unsigned lt = (1u << lane) - 1u;
+    if ((k0 >> lane) & 1u) sv[__popc(k0 & lt)] = cid[0];
+    if ((k1 >> lane) & 1u) sv[__popc(k0) + __popc(k1 & lt)] = cid[1];
+    cnt = __popc(k0) + __popc(k1);
+    __syncwarp();
+  }
+  // survivor slots on 32 lanes: lane l owns slots l and l + 32 (the second pass only runs when more than 32 survive)
   int id[2];
   float s[2];
   bool mine[2];
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const int c = lane + 32 * h;
-    mine[h] = c < TC_CAND && (c % TC_LIST) < ((c < TC_LIST) ? cnt_a : cnt_b);
-    id[h] = mine[h] ? a.cand_i[(size_t)q * TC_CAND + c] : 0x7fffffff;
-    // exact score: the same fp32 fma chain over k = 0..63 as impl 1 and the oracle
+    mine[h] = c < cnt;
+    id[h] = 0x7fffffff;
     s[h] = -INFINITY;
+    if (h == 1 && cnt <= 32) continue;  // warp-uniform
+    if (mine[h]) id[h] = sv[c];
+    // exact score: the same fp32 fma chain over k = 0..63 as impl 1 and the oracle
     if (mine[h]) {
       const float* u = a.ug + (size_t)q * TC_D;
       const float4* it = reinterpret_cast<const float4*>(a.item_emb + (size_t)id[h] * TC_D);
@@ -377,7 +424,6 @@ __global__ void __launch_bounds__(256) tc_rescore_kernel(const RescoreArgs a) {
   for (int h = 0; h < 2; ++h)
     if (mine[h]) mo[rank[h]] = make_float2(s[h], __int_as_float(id[h]));
   __syncwarp();
-  const int K = a.k;
   float ls = -INFINITY;
   int li = -1;
   float thr = -INFINITY;  // score of list slot K-1 (warp-uniform)
@@ -396,8 +442,6 @@ __global__ void __launch_bounds__(256) tc_rescore_kernel(const RescoreArgs a) {
   }
   // exactness test
   const float kth = __shfl_sync(SRB_FULL_MASK, ls, K - 1);
-  const float bmax = __uint_as_float(*a.bmax_bits);
-  const float E = (1.0f / 512.0f + 1.0f / 65536.0f + 1.0f / 262144.0f) * a.unorm[q] * bmax;  // TF32 truncation + slot tags
   const float thr32 = fmaxf(a.cand_thr[(size_t)q * 2], a.cand_thr[(size_t)q * 2 + 1]);
   int deg = 0;
   if (a.rated_ptr) {

@@ -297,6 +297,13 @@ static bool sync_in_kernels() {
   return mode != 0;
 }
 
+// NVLS route of the partial-sum exchange (needs the multicast mapping): partial products stay in the rank's own copy of
+// the staging buffer and the owner reads their sum with multimem.ld_reduce.  Opt-in (srb_shard_desc.nvls; parity-tested
+// like the default): at 2 ranks the in-switch reduction delivered 183 GB/s per GPU and the step took 91 ms against 82 ms
+// with the P2P pushes (profiles/r02o_trace_10M_n2_*.txt) -- it halves a rank's NVLink ingress, which only matters from
+// 4-8 ranks.
+static bool nvls(const Ctx& c) { return c.s->nvls != 0 && c.G > 1 && c.s->sym_mc != nullptr; }
+
 // wait / signal folded into the kernels of a layer (PeerSync in spmm_args.cuh)
 static PeerSync peer_sync(const Ctx& c, bool wait, bool signal) {
   PeerSync p = {};
@@ -456,18 +463,47 @@ static int layer(const Ctx& c, const float* xu, const float* xi, const Epi& e) {
     if (c.G == 1) {
       item_epilogue(c, e, a);
     } else {
-      for (int q = 0; q < c.G; ++q) a.stage_peer[q] = c.symf(c.sp.stage, q);
-      for (int q = 0; q <= c.G; ++q) a.stage_bounds[q] = (int32_t)((int64_t)q * c.I / c.G);
-      a.stage_rank = c.rank;
-      a.stage_cap = c.sp.stage_cap;
+      if (nvls(c)) {  // the partial product stays local: one "owner" covering every row, plain stores
+        a.stage_peer[0] = c.mine(c.sp.stage);
+        a.stage_bounds[0] = 0;
+        for (int q = 1; q <= 8; ++q) a.stage_bounds[q] = c.I;
+        a.stage_rank = 0;
+        a.stage_cap = c.I;
+      } else {
+        for (int q = 0; q < c.G; ++q) a.stage_peer[q] = c.symf(c.sp.stage, q);
+        for (int q = 0; q <= c.G; ++q) a.stage_bounds[q] = (int32_t)((int64_t)q * c.I / c.G);
+        a.stage_rank = c.rank;
+        a.stage_cap = c.sp.stage_cap;
+      }
       // wait: the owners have finished reading the staging areas (and every rank the buffers this layer rewrites);
       // signal: this rank's partial rows are in place
       a.ps = peer_sync(c, true, true);
     }
     SRB_TRY(launch_spmm(a, c.d, c.st));
   }
-  // ---- user half: entirely local (runs while the partial rows drain over NVLink) ----
-  if (c.Ug > 0) {
+  // ---- item half, part 2 (owner-side reduction + epilogue + push to every rank) beside the user half ----
+  // The reduction is NVLink-bound and the user-side product is local compute: with the caller's fork stream the two
+  // run concurrently (the reduction on one CTA per SM), so the exchange hides behind the product.
+  const bool overlap = c.G > 1 && sync_in_kernels() && s->fork_stream && s->fork_event && s->join_event;
+  cudaStream_t rs = overlap ? (cudaStream_t)s->fork_stream : c.st;
+  auto reduce = [&]() -> int {
+    SpmmArgs a;
+    SRB_TRY(base_args(c, s->Rt, c.I, xu, nullptr, a));
+    item_epilogue(c, e, a);
+    ReduceArgs r = {};
+    r.stage = c.mine(c.sp.stage);
+    r.world = c.G;
+    r.stage_cap = c.sp.stage_cap;
+    r.slice_begin = c.ib;
+    r.n_slice = c.ib_end - c.ib;
+    r.mask = e.rows_only ? (const uint32_t*)(c.loc + c.lp.imask) : nullptr;
+    r.mc_part = nvls(c) ? (const float*)((const char*)s->sym_mc + c.sp.stage) : nullptr;
+    r.small_grid = overlap ? 1 : 0;
+    a.ps = peer_sync(c, true, true);  // wait: all partials are in place; signal: the finished rows are everywhere
+    return launch_reduce_rows(a, r, c.d, rs);
+  };
+  auto user_half = [&]() -> int {
+    if (c.Ug <= 0) return SRB_OK;
     SpmmArgs a;
     SRB_TRY(base_args(c, s->Ru, c.Ug, xi, e.mask_i, a));
     if (e.rows_only) use_batch_rows(c, false, a);
@@ -484,25 +520,20 @@ static int layer(const Ctx& c, const float* xu, const float* xi, const Epi& e) {
       a.am = s->mu;
       a.av = s->vu;
     }
-    SRB_TRY(launch_spmm(a, c.d, c.st));
+    return launch_spmm(a, c.d, c.st);
+  };
+  if (c.G == 1) return user_half();
+  if (overlap) {
+    SRB_TRY(check_cuda(cudaEventRecord((cudaEvent_t)s->fork_event, c.st), "shard fork record"));
+    SRB_TRY(check_cuda(cudaStreamWaitEvent(rs, (cudaEvent_t)s->fork_event, 0), "shard fork wait"));
+    SRB_TRY(reduce());      // launched first: its one CTA per SM is resident before the product fills the rest
+    SRB_TRY(user_half());
+    SRB_TRY(check_cuda(cudaEventRecord((cudaEvent_t)s->join_event, rs), "shard join record"));
+    return check_cuda(cudaStreamWaitEvent(c.st, (cudaEvent_t)s->join_event, 0), "shard join wait");
   }
-  if (c.G == 1) return SRB_OK;
-  // ---- item half, part 2: owner-side reduction + epilogue + push to every rank ----
+  SRB_TRY(user_half());  // (runs while the partial rows drain over NVLink)
   if (!sync_in_kernels()) SRB_TRY(barrier(c));
-  {
-    SpmmArgs a;
-    SRB_TRY(base_args(c, s->Rt, c.I, xu, nullptr, a));
-    item_epilogue(c, e, a);
-    ReduceArgs r;
-    r.stage = c.mine(c.sp.stage);
-    r.world = c.G;
-    r.stage_cap = c.sp.stage_cap;
-    r.slice_begin = c.ib;
-    r.n_slice = c.ib_end - c.ib;
-    r.mask = e.rows_only ? (const uint32_t*)(c.loc + c.lp.imask) : nullptr;
-    a.ps = peer_sync(c, true, true);  // wait: all partials have landed; signal: the finished rows are everywhere
-    SRB_TRY(launch_reduce_rows(a, r, c.d, c.st));
-  }
+  SRB_TRY(reduce());
   return sync_in_kernels() ? SRB_OK : barrier(c);
 }
 

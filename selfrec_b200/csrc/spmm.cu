@@ -321,7 +321,9 @@ __global__ void __launch_bounds__(256) spmm_hub_kernel(const SpmmArgs a) {
       beg = min(rend, rbeg + ci * SRB_HUB_CHUNK);
       end = min(rend, beg + SRB_HUB_CHUNK);
     }
-    constexpr int per = SRB_HUB_CHUNK / 8;  // non-zeros per warp, a multiple of 32 (segments are at most a chunk long)
+    // non-zeros per warp: a multiple of 32, the segment spread over all 8 warps (column-blocked segments and the last
+    // chunk of a row are shorter than a full chunk; with a fixed 256 per warp most warps of such a CTA sat idle)
+    const int per = ((end - beg + 255) / 256) * 32;
     const int wbeg = beg + wib * per;
     const int wend = min(end, wbeg + per);
     float4 acc0 = f4_zero(), acc1 = f4_zero();
@@ -485,6 +487,16 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmArgs a) {
   peer_signal(a.ps);  // (sharded item-side product: this rank's partial rows are in the owners' staging areas)
 }
 
+// sum over the ranks' copies of a multicast-mapped buffer, added by the NVSwitch (NVLS): 16 bytes per request
+__device__ __forceinline__ float4 multimem_ld_reduce_add4(const float* mc) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(mc)
+               : "memory");
+  return v;
+}
+
 // Owner-side reduction of an item slice (bipartite sharding): every rank's item-side product left its partial rows
 // in this rank's staging area; one lane group per slice row adds them in rank order (deterministic, and the only
 // writer of the row) and runs the common epilogue -- noise, layer sum, Adam, and the pushes that hand the finished
@@ -501,6 +513,37 @@ __global__ void __launch_bounds__(256) reduce_rows_kernel(const SpmmArgs a, cons
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int n_items = (r.n_slice + RPW - 1) / RPW;
   peer_wait(a.ps);  // every rank's partial rows have landed in the staging area
+  if (r.mc_part) {
+    // NVLS route: four rows per lane group in flight (8 x 16 B per lane): the kernel is bound by NVLink latency x
+    // bytes in flight and runs on one CTA per SM beside the user-side SpMM
+    constexpr int UN = 4;
+    for (int item = warp0 * UN; item < n_items; item += nwarps * UN) {
+      float4 p0[UN], p1[UN];
+      bool ok[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int k = (item + u) * RPW + grp;
+        ok[u] = (item + u) < n_items && k < r.n_slice;
+        if (ok[u] && r.mask) {
+          const int row = r.slice_begin + k;
+          ok[u] = (__ldg(r.mask + (row >> 5)) >> (row & 31)) & 1u;
+        }
+        p0[u] = p1[u] = f4_zero();
+        if (ok[u]) {
+          const float* src = r.mc_part + (size_t)(r.slice_begin + k) * D + gl * 4;
+          p0[u] = multimem_ld_reduce_add4(src);
+          p1[u] = multimem_ld_reduce_add4(src + HALF);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        if (!__any_sync(SRB_FULL_MASK, ok[u])) continue;
+        spmm_epilogue<D>(a, r.slice_begin + (item + u) * RPW + grp, gl, p0[u], p1[u], ok[u]);
+      }
+    }
+    peer_signal(a.ps);
+    return;
+  }
   for (int item = warp0; item < n_items; item += nwarps) {
     const int k = item * RPW + grp;
     bool valid = k < r.n_slice;
@@ -580,7 +623,7 @@ int launch_reduce_rows(const SpmmArgs& a, const ReduceArgs& r, int d, cudaStream
   if (r.n_slice <= 0) return SRB_OK;
   const int rpw = 32 / (d / 8);
   long long blocks = ((long long)(r.n_slice + rpw - 1) / rpw + 7) / 8;
-  const long long cap = (long long)sm_count() * 8;
+  const long long cap = (long long)sm_count() * (r.small_grid ? 1 : 8);
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   switch (d) {

@@ -132,6 +132,11 @@ struct ReduceArgs {
   int32_t slice_begin;  // item id of slice row 0 (epilogue tensors are indexed by item id)
   int32_t n_slice;
   const uint32_t* mask; // optional bitmap over item ids: only the rows whose bit is set are reduced (batch rows of the last layer)
+  // NVLS route: every rank left its partial product in ITS OWN copy of a multicast-mapped [n_items, D] buffer; mc_part is
+  // the multicast address of that buffer, and one multimem.ld_reduce per 16 bytes returns the sum over all ranks, added
+  // inside the NVSwitch -- the owner receives one reduced row instead of world - 1 partial rows
+  const float* mc_part;
+  int32_t small_grid;   // the kernel runs beside the user-side SpMM and is NVLink-bound: a CTA or two per SM
 };
 
 int launch_spmm(const SpmmArgs& a, int d, cudaStream_t st);

@@ -12,7 +12,7 @@ def max_rel(a, b):
     return float((a - b).abs().max().item()) / max(den, 1e-30)
 
 
-def sharded_vs_single(model, data, d, L, B, batches, *, steps=3, lr=1e-3, reg=1e-4, seed=7, dev=None, multicast=None, **kw):
+def sharded_vs_single(model, data, d, L, B, batches, *, steps=3, lr=1e-3, reg=1e-4, seed=7, dev=None, multicast=None, nvls=None, **kw):
     """Collective over the default process group (or single-process).  Runs `steps` steps of ShardedEngine on all
     ranks and of TrainEngine on every rank (the reference replica), on batches[k] (device int32 rows).
     Returns dict(loss_rel, m_*_rel, v_*_rel, final_*_rel, user_rel, item_rel, upd_off_frac, max_rel, ...) -- maxima
@@ -26,7 +26,7 @@ def sharded_vs_single(model, data, d, L, B, batches, *, steps=3, lr=1e-3, reg=1e
     g = torch.Generator(device=dev).manual_seed(1234)
     iu = torch.empty((U, d), device=dev).uniform_(-0.1, 0.1, generator=g)
     ii = torch.empty((I, d), device=dev).uniform_(-0.1, 0.1, generator=g)
-    sh = ShardedEngine(model, data, d, L, B, lr, reg, init_user=iu, init_item=ii, philox_seed=seed, device=dev, multicast=multicast, **kw)
+    sh = ShardedEngine(model, data, d, L, B, lr, reg, init_user=iu, init_item=ii, philox_seed=seed, device=dev, multicast=multicast, nvls=nvls, **kw)
     ref = TrainEngine(model, data, d, L, B, lr, reg, init_user=iu, init_item=ii, philox_seed=seed, device=dev, **kw)
     # Parity is asserted on well-conditioned quantities: the losses, Adam's first moment m (linear in the gradient:
     # after step 1, m = 0.1 g) and second moment, and the clean forward.  The PARAMETERS themselves are compared in two
@@ -78,7 +78,7 @@ def sharded_vs_single(model, data, d, L, B, batches, *, steps=3, lr=1e-3, reg=1e
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         out = {k: float(v) for k, v in zip(sorted(out), t.tolist())}
     out["world"] = sh.world
-    out["route"] = "multicast" if sh.use_multicast else ("unicast" if sh.world > 1 else "single")
+    out["route"] = ("nvls" if sh.use_nvls else "multicast") if sh.use_multicast else ("unicast" if sh.world > 1 else "single")
     out["steps"] = steps
     out["max_rel"] = max(out["loss_rel"], out["m_user_rel"], out["m_item_rel"], out["v_user_rel"], out["v_item_rel"],
                          out["final_user_rel"], out["final_item_rel"])

@@ -82,7 +82,7 @@ class ShardedEngine:
     philox_seed draws the noise the single-GPU TrainEngine draws."""
 
     def __init__(self, model, data, emb_size, n_layers, batch_size, lr, reg, *, eps=0.0, tau=0.2, cl_rate=0.0, layer_cl=0,
-                 l2_div=1.0, init_user=None, init_item=None, group=None, philox_seed=0x5EED, device=None, multicast=None):
+                 l2_div=1.0, init_user=None, init_item=None, group=None, philox_seed=0x5EED, device=None, multicast=None, nvls=None):
         import torch
         from . import ops
         lib = _lib.require_device()
@@ -195,6 +195,17 @@ class ShardedEngine:
         s.sym_mc = mc_ptr or None
         s.sym_bytes = int(lay.sym_bytes)
         s.workspace, s.workspace_bytes = C.c_void_p(ws_ptr), int(lay.workspace_bytes)
+        if self.world > 1 and os.environ.get("SRB_SHARD_OVERLAP", "1") != "0":
+            # the owner-side reduction of a layer runs on this stream beside the user-side product
+            self._fork_stream = torch.cuda.Stream(device=dev)
+            self._fork_events = (torch.cuda.Event(), torch.cuda.Event())
+            for ev in self._fork_events:
+                ev.record(self._fork_stream)  # torch creates the CUDA event lazily, on first record
+            s.fork_stream = C.c_void_p(self._fork_stream.cuda_stream)
+            s.fork_event, s.join_event = (C.c_void_p(ev.cuda_event) for ev in self._fork_events)
+        want_nvls = (os.environ.get("SRB_SHARD_NVLS", "0") == "1") if nvls is None else bool(nvls)
+        s.nvls = 1 if (want_nvls and mc_ptr) else 0
+        self.use_nvls = bool(s.nvls)
         self.desc = s
         self.graph = None
         self._warm = False

@@ -33,14 +33,15 @@ def main():
              ("LightGCN", 64, 3, dict(l2_div=512.0))]
     graphs = {"powerlaw": synth.make_interaction((3000, 4000, 60000), seed=3),
               "zipf-split-rows": synth.make_device_interaction((30000, 8000, 1200000), seed=2, alpha=1.1)}
-    routes = [None] if world == 1 else [False, True]
+    routes = [None] if world == 1 else [False, True, "nvls"]  # P2P stores | multicast stores | + in-switch reduce-scatter
     for gname, data in graphs.items():
         B = 512
         batches = device_batches(data, B, 3, seed=5)
         for model, d, L, kw0 in cases:
             for mc, strict in [(m, s) for m in routes for s in ((True, False) if "eps" in kw0 else (True,))]:
                 kw = dict(kw0, eps=0.0) if (strict and "eps" in kw0) else kw0
-                r = sharded_vs_single(model, data, d, L, B, batches, steps=3, multicast=mc, **kw)
+                r = sharded_vs_single(model, data, d, L, B, batches, steps=3, multicast=bool(mc), nvls=(mc == "nvls"), **kw) if mc is not None else \
+                    sharded_vs_single(model, data, d, L, B, batches, steps=3, **kw)
                 if strict:
                     good = r["max_rel"] <= TOL and r["m_rows_off_frac"] == 0.0
                 else:
