@@ -1,6 +1,7 @@
 """Launched by torchrun (one rank per GPU) or directly (world 1): the bipartite-sharded step must follow the
 single-GPU fused engine -- same losses, same Adam moments, same clean forward -- on the same batches and the same
-Philox noise, for XSimGCL, SimGCL and LightGCN, on both peer-store routes (unicast P2P and NVSwitch multicast).
+Philox noise, for XSimGCL, SimGCL and LightGCN, on both peer-store routes (unicast P2P and NVSwitch multicast) and, at
+2 ranks, with the optional NVLS reduce-scatter (multimem.ld_reduce).
 
 Two passes per case.  eps = 0: strict, every compared quantity within 1e-4.  eps as configured: the perturbation
 sign(y) * noise * eps (XSimGCL.py:90-91) is discontinuous at y = 0, so an element within fp32 rounding of zero flips
@@ -33,7 +34,8 @@ def main():
              ("LightGCN", 64, 3, dict(l2_div=512.0))]
     graphs = {"powerlaw": synth.make_interaction((3000, 4000, 60000), seed=3),
               "zipf-split-rows": synth.make_device_interaction((30000, 8000, 1200000), seed=2, alpha=1.1)}
-    routes = [None] if world == 1 else [False, True, "nvls"]  # P2P stores | multicast stores | + in-switch reduce-scatter
+    # P2P stores | multicast stores | + in-switch reduce-scatter (the optional NVLS route, exercised at 2 ranks)
+    routes = [None] if world == 1 else ([False, True, "nvls"] if world == 2 else [False, True])
     for gname, data in graphs.items():
         B = 512
         batches = device_batches(data, B, 3, seed=5)

@@ -49,6 +49,25 @@ int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(srb_spmm_desc)
     mine = [C.sizeof(t) for t in (_lib.SpmmDesc, _lib.EncoderDesc, _lib.BprDesc, _lib.InfoNceProblem, _lib.InfoNceDesc,
                                   _lib.TopkDesc, _lib.StepDesc, _lib.SpmmShardedDesc)]
     assert mine == sizes
+    # the descriptors of the sharded step and the fields added last (a mirror that is one field short still has the
+    # right size when padding absorbs it, so the tail offsets are compared too)
+    src2 = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "selfrec_b200.h"
+int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(srb_shard_desc), sizeof(srb_graph_csr), sizeof(srb_hub_split),
+ sizeof(srb_shard_layout), offsetof(srb_shard_desc, nvls), offsetof(srb_shard_desc, fork_stream), offsetof(srb_shard_desc, Rt),
+ offsetof(srb_step_desc, fork_stream), offsetof(srb_encoder_desc, x1));return 0;}
+'''
+    with tempfile.TemporaryDirectory() as td:
+        c = os.path.join(td, "probe2.c")
+        open(c, "w").write(src2)
+        exe = os.path.join(td, "probe2")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        want = [int(x) for x in subprocess.check_output([exe]).split()]
+    got = [C.sizeof(_lib.ShardDesc), C.sizeof(_lib.GraphCsr), C.sizeof(_lib.HubSplit), C.sizeof(_lib.ShardLayout), _lib.ShardDesc.nvls.offset,
+           _lib.ShardDesc.fork_stream.offset, _lib.ShardDesc.Rt.offset, _lib.StepDesc.fork_stream.offset, _lib.EncoderDesc.x1.offset]
+    assert got == want
 
 
 def test_no_cpu_fallback(built_lib):
