@@ -5,7 +5,8 @@
 * the exactness certificate of the tcgen05 ranking path (csrc/score_topk_tc.cu): with TF32-truncated operands
   every approximate score is within E = (2^-9 + 2^-16 + 2^-18) * ||u|| * max||i|| of the exact one, so if the best
   non-candidate bound max(thr_A, thr_B) + E is below the exact k-th score, the true top-k lies inside the
-  2 x 24 candidates -- whatever the data.
+  2 x 24 candidates -- whatever the data; and the pruning rule of tc_rescore_kernel (drop candidates whose approximate
+  score is below a_K - 2E) never removes a member of the exact top-K.
 """
 import numpy as np
 import pytest
@@ -93,6 +94,41 @@ def test_ranking_certificate_is_sound(spread):
         assert certified == n_u  # well-separated scores: nobody needs the fallback
 
 
+@pytest.mark.parametrize("spread", [1.0, 1e-2, 1e-4])
+def test_rescore_pruning_never_drops_a_topk_member(spread):
+    """tc_rescore_kernel prunes before the exact pass: with a_K the K-th largest APPROXIMATE score of a user's candidates,
+    every candidate whose approximate score is below a_K - 2E is dropped (E bounds |approx - exact|).  numpy model of
+    that rule on TF32-truncated scores: the exact top-K of the candidate set always survives, tight scores included
+    (then nothing is pruned), and on separated scores roughly half of the 48 candidates go."""
+    rng = np.random.default_rng(7 + int(1 / spread))
+    n_u, n_i, d, k = 64, 3000, 64, 20
+    base = rng.standard_normal(d).astype(np.float32)
+    U = (base + spread * rng.standard_normal((n_u, d))).astype(np.float32)
+    I = (base + spread * rng.standard_normal((n_i, d))).astype(np.float32)
+    approx = (tf32_trunc(U).astype(np.float64) @ tf32_trunc(I).astype(np.float64).T).astype(np.float32)
+    exact = U.astype(np.float64) @ I.astype(np.float64).T
+    bmax = np.linalg.norm(I.astype(np.float64), axis=1).max()
+    col_half = (np.arange(n_i) // 64) % 2
+    kept_total = cand_total = 0
+    for q in range(n_u):
+        cand = []
+        for h in (0, 1):
+            cols = np.flatnonzero(col_half == h)
+            cand += list(cols[np.argsort(-approx[q, cols], kind="stable")][:24])
+        cand = np.array(cand)
+        E = np.float32((2.0 ** -9 + 2.0 ** -16 + 2.0 ** -18) * np.linalg.norm(U[q].astype(np.float64)) * bmax)
+        assert np.abs(approx[q, cand] - exact[q, cand]).max() <= E  # the premise of the rule
+        a_sorted = np.sort(approx[q, cand])[::-1]
+        cut = a_sorted[k - 1] - np.float32(2.0) * E                  # the kernel's fp32 arithmetic
+        keep = cand[approx[q, cand] >= cut]
+        truth = cand[np.argsort(-exact[q, cand], kind="stable")][:k]
+        assert set(truth.tolist()) <= set(keep.tolist()), (spread, q)
+        kept_total += len(keep)
+        cand_total += len(cand)
+    if spread == 1.0:
+        assert kept_total < 0.75 * cand_total  # separated scores: the rule removes a good part of the exact work
+
+
 @pytest.mark.parametrize("tau", [0.5, 0.2, 0.05, 0.025])
 def test_fixed_shift_logsumexp_model(tau):
     """InfoNCE pass A (csrc/infonce_tc.cuh) shifts every logit by the bound 1/tau of a cosine logit instead of a
@@ -113,3 +149,45 @@ def test_fixed_shift_logsumexp_model(tau):
     got = shift + np.log(l, dtype=np.float32)
     assert np.isfinite(got).all() and (l > 0).all()
     assert np.abs(got - ref).max() <= 4e-7 / tau + 1e-6
+
+
+def _philox4x32_10(ctr, key):
+    """Philox4x32-10 (Salmon et al. 2011) on uint32 arrays: the generator of csrc/common.cuh."""
+    M0, M1, W0, W1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint32(0x9E3779B9), np.uint32(0xBB67AE85)
+    c = [np.asarray(x, dtype=np.uint32) for x in ctr]
+    k0, k1 = np.uint32(key[0]), np.uint32(key[1])
+    for _ in range(10):
+        p0 = M0 * c[0].astype(np.uint64)
+        p1 = M1 * c[2].astype(np.uint64)
+        hi0, lo0 = (p0 >> np.uint64(32)).astype(np.uint32), p0.astype(np.uint32)
+        hi1, lo1 = (p1 >> np.uint64(32)).astype(np.uint32), p1.astype(np.uint32)
+        c = [hi1 ^ c[1] ^ k0, lo1, hi0 ^ c[3] ^ k1, lo0]
+        k0, k1 = np.uint32((int(k0) + int(W0)) & 0xFFFFFFFF), np.uint32((int(k1) + int(W1)) & 0xFFFFFFFF)
+    return np.stack(c, -1)
+
+
+def test_philox_counter_layout_keeps_view_and_step_streams_apart():
+    """Perf-mode noise of the SpMM epilogue (csrc/spmm.cu): counter = (row, column block | view << 16, layer tag, step),
+    key = seed.  Every (view, step) pair must be its own stream (the reference draws fresh noise on every perturbed
+    forward, SimGCL.py:87-88).  The round-1 layout put view ^ step into ONE counter word, which made (view 1, step s)
+    equal (view 0, step s ^ 1): the model shows that collision and that the current layout has none."""
+    rows = np.arange(64, dtype=np.uint32)
+    colblk, layer_tag, key = np.uint32(3), np.uint32(0x10), (0x5EED, 0x1234)
+
+    def current(view, step):
+        z = np.zeros_like(rows)
+        return _philox4x32_10((rows, z + (colblk | np.uint32(view << 16)), z + layer_tag, z + np.uint32(step)), key)
+
+    def round1(view, step):  # counter word 3 = view ^ step
+        z = np.zeros_like(rows)
+        return _philox4x32_10((rows, z + colblk, z + layer_tag, z + np.uint32(view ^ step)), key)
+
+    streams = {(v, s): current(v, s) for v in (0, 1) for s in range(6)}
+    keys = list(streams)
+    for a in range(len(keys)):
+        for b in range(a + 1, len(keys)):
+            assert not np.array_equal(streams[keys[a]], streams[keys[b]]), (keys[a], keys[b])
+    assert np.array_equal(round1(1, 2), round1(0, 3))  # what the advisor found
+    # known-answer vector of Philox4x32-10 (Random123 kat_vectors: counter 0, key 0)
+    z = np.zeros(1, dtype=np.uint32)
+    assert _philox4x32_10((z, z, z, z), (0, 0))[0].tolist() == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
