@@ -53,7 +53,7 @@ int srb_device_ok(void);
  * per chunk writes its partial sum to `part`, and the row's owner adds the partials in chunk order (deterministic).
  * Static lists (built with the graph): the first n_rows entries of row_order are the split rows, first[r] is the
  * slot of row r's first chunk, work[w] = (row, chunk index), n_work chunks in total.  Device-classified lists
- * (srb_build_batch_rows): first / work are written on the device, n_work is the capacity and the live counts come
+ * (the batch rows of a training step): first / work are written on the device, n_work is the capacity and the live counts come
  * from n_vlong_dev[0] (rows) and n_vlong_dev[4] (chunks). */
 #define SRB_HUB_CHUNK 2048
 #define SRB_HUB_MIN_NNZ 4096
@@ -353,18 +353,6 @@ int srb_topk_rows(const float* scores, int32_t n_q, int32_t n_items, int32_t k, 
  * exactly as CPython would. */
 int srb_random_sample_range(uint32_t* mt625, int64_t n, int64_t k, int32_t use_pool, int64_t* out);
 
-/* Rows of the [N, d] tables a batch touches (u, U + i, U + j; batch = srb_sampler_next_batch layout), each listed
- * ONCE, for srb_spmm_desc.n_vlong_dev: rows[4][3*batch_cap] by degree class (split rows, a CTA per long row, a warp per
- * other row), counters[8]: [0..3] class sizes, [4] chunks of the split rows; row_mask ((n_total_rows+31)/32 words,
- * required: it is also what de-duplicates the list) = bitmap of all batch rows for srb_spmm_desc.col_mask.
- * hub_first[3*batch_cap] / hub_work[hub_work_cap][2] (optional) receive the split-row lists; without them long rows
- * get a CTA each.  Row-sharded tables: only rows in [row_begin, row_begin + n_local_rows) are listed, as local ids
- * of the rank's CSR slice (rowptr).  This is what lets the last forward layer of a training step (nothing but the
- * batch rows of the final mean is read, XSimGCL.py:30,45-50) skip every other row. */
-int srb_build_batch_rows(const int32_t* batch, int32_t batch_cap, int32_t n_users, const int32_t* rowptr,
-                         int32_t row_begin, int32_t n_local_rows, int32_t n_total_rows, int32_t* rows,
-                         int32_t* counters, uint32_t* row_mask, int32_t* hub_first, int32_t* hub_work,
-                         int32_t hub_work_cap, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Native dataset -> CSR builder (host C++).  Replaces the Python loops of
@@ -555,28 +543,6 @@ int64_t srb_sampler_pairs(const srb_sampler* s);
 int srb_sampler_ring_start(srb_sampler* s, int32_t batch_size, int32_t batch_cap, int32_t depth);
 int srb_sampler_ring_pop(srb_sampler* s, int32_t* out);
 int srb_sampler_ring_stop(srb_sampler* s);
-
-/* ---------------------------------------------------------------------------------------
- * Row-sharded multi-GPU propagation.  Rank r owns the contiguous row block
- * [row_begin, row_begin + local.n_rows) of the [n_cols, d] tables and the CSR slice A[R_r, :]
- * (local.rowptr rebased to 0, column ids global).  Every dense operand of `local` (X, Y, extra,
- * noise, sum_in/out, adam p/m/v) is a full [n_cols, d] buffer indexed by GLOBAL row.  The
- * epilogue stores each finished row into every rank's copy over NVLink P2P mappings (peer
- * pointers from torch.distributed._symmetric_memory), so the per-layer all-gather is fused into
- * the SpMM: peer_Y the layer output, peer_sum the running layer sum, peer_p the Adam-updated
- * parameters.  NULL arrays disable the respective push.  A cross-rank barrier must separate the
- * call from the consumers of the pushed rows.
- * ------------------------------------------------------------------------------------- */
-typedef struct srb_spmm_sharded_desc {
-  srb_spmm_desc local;
-  int32_t row_begin;
-  int32_t world;
-  float* peer_Y[8];
-  float* peer_sum[8];
-  float* peer_p[8];
-} srb_spmm_sharded_desc;
-
-int srb_spmm_csr_allgather(const srb_spmm_sharded_desc* desc, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Bipartite-sharded training step (selfrec_b200/csrc/sharded.cu).  One process per GPU.

@@ -138,11 +138,6 @@ class ShardLayout(C.Structure):
                 ("ctrl", C.c_int64)]
 
 
-class SpmmShardedDesc(C.Structure):
-    _fields_ = [("local", SpmmDesc), ("row_begin", C.c_int32), ("world", C.c_int32), ("peer_Y", VP * 8), ("peer_sum", VP * 8),
-                ("peer_p", VP * 8)]
-
-
 MODEL_IDS = {"MF": 0, "LightGCN": 1, "SimGCL": 2, "XSimGCL": 3, "SGL": 4}
 BATCH_HEADER = 4
 
@@ -164,7 +159,6 @@ SYMBOLS = {
     "srb_scatter_add_segments": (C.c_int, [VP, C.c_int32, C.c_int32, VP, VP]),
     "srb_rank_hit_masks": (C.c_int, [VP, C.c_int32, C.c_int32, VP, VP, VP, VP, VP]),
     "srb_random_sample_range": (C.c_int, [VP, C.c_int64, C.c_int64, C.c_int32, VP]),
-    "srb_build_batch_rows": (C.c_int, [VP, C.c_int32, C.c_int32, VP, C.c_int32, C.c_int32, C.c_int32, VP, VP, VP, VP, VP, C.c_int32, VP]),
     "srb_dataset_load": (VP, [C.c_char_p, C.c_char_p]),
     "srb_dataset_free": (None, [VP]),
     "srb_dataset_counts": (C.c_int, [VP, VP]),
@@ -196,7 +190,6 @@ SYMBOLS = {
     "srb_sampler_ring_start": (C.c_int, [VP, C.c_int32, C.c_int32, C.c_int32]),
     "srb_sampler_ring_pop": (C.c_int, [VP, c_i32p]),
     "srb_sampler_ring_stop": (C.c_int, [VP]),
-    "srb_spmm_csr_allgather": (C.c_int, [C.POINTER(SpmmShardedDesc), VP]),
     "srb_shard_plan": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(ShardLayout)]),
     "srb_shard_step": (C.c_int, [C.POINTER(ShardDesc), VP]),
     "srb_shard_forward": (C.c_int, [C.POINTER(ShardDesc), VP, VP]),

@@ -583,18 +583,3 @@ extern "C" int srb_train_step(const srb_step_desc* s, void* stream) {
   }
   return run_chain(s, w, c, &gd_live, true, st);
 }
-
-extern "C" int srb_build_batch_rows(const int32_t* batch, int32_t batch_cap, int32_t n_users, const int32_t* rowptr, int32_t row_begin,
-                                    int32_t n_local_rows, int32_t n_total_rows, int32_t* rows, int32_t* counters, uint32_t* row_mask,
-                                    int32_t* hub_first, int32_t* hub_work, int32_t hub_work_cap, void* stream) {
-  SRB_REQUIRE(batch && rowptr && rows && counters && row_mask, "build_batch_rows: null pointer");
-  SRB_REQUIRE(batch_cap > 0 && row_begin >= 0 && n_local_rows >= 0 && row_begin + n_local_rows <= n_total_rows,
-              "build_batch_rows: bad shape");
-  SRB_REQUIRE(!hub_first || (hub_work && hub_work_cap > 0), "build_batch_rows: split-row lists incomplete");
-  cudaStream_t st = (cudaStream_t)stream;
-  SRB_TRY(srb::check_cuda(cudaMemsetAsync(counters, 0, 32, st), "batch rows memset"));
-  SRB_TRY(srb::check_cuda(cudaMemsetAsync(row_mask, 0, (size_t)((n_total_rows + 31) / 32) * 4, st), "row mask memset"));
-  srb::build_batch_rows_kernel<<<(3 * batch_cap + 255) / 256, 256, 0, st>>>(batch, batch_cap, n_users, rowptr, row_begin, n_local_rows,
-                                                                           rows, counters, row_mask, hub_first, hub_work, hub_work_cap);
-  return srb::post_launch("build_batch_rows_kernel");
-}

@@ -778,32 +778,6 @@ extern "C" int srb_spmm_epilogue_rows(const srb_spmm_desc* desc, void* stream) {
   return srb::launch_rows_epilogue(a, desc->d, (cudaStream_t)stream);
 }
 
-extern "C" int srb_spmm_csr_allgather(const srb_spmm_sharded_desc* desc, void* stream) {
-  SRB_REQUIRE(desc != nullptr, "spmm_allgather: null desc");
-  SRB_REQUIRE(desc->world >= 1 && desc->world <= 8, "spmm_allgather: world must be 1..8");
-  // (with a device-classified row list n_rows is the list capacity, not the number of owned rows)
-  SRB_REQUIRE(desc->row_begin >= 0 && (desc->local.n_vlong_dev || desc->row_begin + desc->local.n_rows <= desc->local.n_cols),
-              "spmm_allgather: owned rows [%d, %d) outside [0, %d)", desc->row_begin, desc->row_begin + desc->local.n_rows,
-              desc->local.n_cols);
-  srb::SpmmArgs a;
-  SRB_TRY(srb::fill_args(&desc->local, a));
-  a.world = desc->world;
-  a.row_begin = desc->row_begin;
-  const bool has_y = desc->peer_Y[0] != nullptr, has_s = desc->peer_sum[0] != nullptr, has_p = desc->peer_p[0] != nullptr;
-  SRB_REQUIRE(!has_s || desc->local.sum_out, "spmm_allgather: peer_sum needs the sum epilogue");
-  SRB_REQUIRE(!has_p || desc->local.adam_p, "spmm_allgather: peer_p needs the Adam epilogue");
-  for (int g = 0; g < desc->world; ++g) {
-    SRB_REQUIRE((desc->peer_Y[g] != nullptr) == has_y && (desc->peer_sum[g] != nullptr) == has_s &&
-                    (desc->peer_p[g] != nullptr) == has_p,
-                "spmm_allgather: peer buffer %d inconsistent", g);
-    SRB_REQUIRE(!has_y || desc->peer_Y[g] != desc->local.X, "spmm_allgather: peer buffer aliases X");
-    a.peer[g] = desc->peer_Y[g];
-    a.peer_sum[g] = desc->peer_sum[g];
-    a.peer_p[g] = desc->peer_p[g];
-  }
-  return srb::launch_spmm(a, desc->local.d, (cudaStream_t)stream);
-}
-
 extern "C" int srb_encoder_forward(const srb_encoder_desc* e, void* stream) {
   SRB_REQUIRE(e != nullptr, "encoder: null desc");
   SRB_REQUIRE(e->E0 && e->final_out, "encoder: null E0/final_out");

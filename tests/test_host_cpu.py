@@ -37,7 +37,7 @@ def test_struct_layouts_match_header(built_lib):
 #include <stdio.h>
 #include "selfrec_b200.h"
 int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(srb_spmm_desc), sizeof(srb_encoder_desc), sizeof(srb_bpr_desc),
- sizeof(srb_infonce_problem), sizeof(srb_infonce_desc), sizeof(srb_topk_desc), sizeof(srb_step_desc), sizeof(srb_spmm_sharded_desc));return 0;}
+ sizeof(srb_infonce_problem), sizeof(srb_infonce_desc), sizeof(srb_topk_desc), sizeof(srb_step_desc), sizeof(srb_shard_desc));return 0;}
 '''
     with tempfile.TemporaryDirectory() as td:
         c = os.path.join(td, "probe.c")
@@ -47,7 +47,7 @@ int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(srb_spmm_desc)
         sizes = [int(x) for x in subprocess.check_output([exe]).split()]
     import ctypes as C
     mine = [C.sizeof(t) for t in (_lib.SpmmDesc, _lib.EncoderDesc, _lib.BprDesc, _lib.InfoNceProblem, _lib.InfoNceDesc,
-                                  _lib.TopkDesc, _lib.StepDesc, _lib.SpmmShardedDesc)]
+                                  _lib.TopkDesc, _lib.StepDesc, _lib.ShardDesc)]
     assert mine == sizes
     # the descriptors of the sharded step and the fields added last (a mirror that is one field short still has the
     # right size when padding absorbs it, so the tail offsets are compared too)
@@ -356,7 +356,7 @@ def test_ctypes_structs_match_the_header_layout(tmp_path):
     pairs = {"srb_spmm_desc": _lib.SpmmDesc, "srb_encoder_desc": _lib.EncoderDesc, "srb_scatter_seg": _lib.ScatterSeg,
              "srb_bpr_desc": _lib.BprDesc, "srb_infonce_problem": _lib.InfoNceProblem, "srb_infonce_desc": _lib.InfoNceDesc,
              "srb_topk_desc": _lib.TopkDesc, "srb_graph_csr": _lib.GraphCsr, "srb_step_desc": _lib.StepDesc,
-             "srb_spmm_sharded_desc": _lib.SpmmShardedDesc}
+             "srb_hub_split": _lib.HubSplit, "srb_shard_desc": _lib.ShardDesc, "srb_shard_layout": _lib.ShardLayout}
     cc = shutil.which("gcc") or shutil.which("cc")
     assert cc, "a C compiler is part of the toolchain"
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "selfrec_b200.h"', 'int main(void) {']
