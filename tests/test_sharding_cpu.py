@@ -116,3 +116,90 @@ def test_bipartite_sharded_propagation_world2_gloo():
         p.join(120)
         assert p.exitcode == 0
     assert ret.get(timeout=5) == 1.0
+
+
+def test_sharded_simgcl_step_algebra_model():
+    """float64 model of what csrc/sharded.cu computes for one SimGCL step on G ranks -- cyclic users, replicated items,
+    item rows as rank-ordered sums of partial products, ONE shared first product + per-view noise (SimGCL.py:85-88), the
+    last forward layer evaluated on the batch rows only, one merged backward chain whose first product is masked by the
+    batch rows -- against the oracle's plain restatement of SimGCL.py:25-36 (three full encoders, three backward chains).
+    Losses and the E0 gradient must agree to float64 rounding: the rewrites are algebra, not approximations."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle
+    from selfrec_b200.sharded import extract_blocks, local_user_count
+    import torch
+    U, I, d, L, G, B = 90, 40, 8, 3, 4, 24
+    R, A = _bipartite(U, I, 700, 11)
+    A = oracle.normalize_graph_mat(A)  # symmetric normalisation, like the real adjacency
+    # (the reference's fp32 products (d_r * a) * d_c round the two triangles differently by an ulp; the CUDA backward
+    # reuses A for A^T, which the 1e-4 parity budget absorbs -- here the matrix is made exactly symmetric so that the
+    # model can be held to float64 rounding)
+    A = ((A.astype(np.float64) + A.astype(np.float64).T) * 0.5).astype(np.float32).tocsr()
+    A.sort_indices()
+    rng = np.random.default_rng(3)
+    E0 = rng.standard_normal((U + I, d)) * 0.1
+    noise = rng.random((2, L, U + I, d))
+    eps, tau, lam, reg = 0.1, 0.2, 0.5, 1e-4
+    u_idx, i_idx, j_idx = rng.integers(0, U, B), rng.integers(0, I, B), rng.integers(0, I, B)
+    rp, ci, vv = (torch.from_numpy(np.asarray(x)) for x in (A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data.astype(np.float32)))
+    blocks = []
+    for g in range(G):
+        (p1, c1, v1), (p2, c2, v2) = extract_blocks(rp, ci, vv, U, I, g, G)
+        ug = local_user_count(U, g, G)
+        blocks.append((sp.csr_matrix((v1.numpy().astype(np.float64), c1.numpy(), p1.numpy()), shape=(ug, I)),
+                       sp.csr_matrix((v2.numpy().astype(np.float64), c2.numpy(), p2.numpy()), shape=(I, ug))))
+    A64 = sp.csr_matrix((A.data.astype(np.float32).astype(np.float64), A.indices, A.indptr), shape=A.shape)  # the fp32 values the blocks hold
+    ref = oracle.train_step("SimGCL", A64, E0, U, u_idx, i_idx, j_idx, n_layers=L, reg=reg, batch_size=B, eps=eps, tau=tau, cl_rate=lam,
+                            noise=noise)
+
+    def layer(xu, xi):
+        """xu: list of per-rank user blocks, xi: replicated item table -> (yu list, yi)."""
+        yi = sum(blocks[g][1] @ xu[g] for g in range(G))  # partial products added in rank order by the slice owners
+        return [blocks[g][0] @ xi for g in range(G)], yi
+
+    split = lambda X: ([X[:U][g::G] for g in range(G)], X[U:])
+
+    def join(xu, xi):
+        X = np.empty((U + I, xi.shape[1]))
+        for g in range(G):
+            X[:U][g::G] = xu[g]
+        X[U:] = xi
+        return X
+
+    # ---- forward: one shared first product, noise per view, last layer on the batch rows only ----
+    z = join(*layer(*split(E0)))
+    rows = np.unique(np.concatenate([u_idx, U + i_idx, U + j_idx]))
+    finals = []
+    for view in (None, 0, 1):
+        x = z if view is None else oracle.perturb(z, noise[view][0], eps)
+        acc = x.copy()
+        for k in range(1, L):
+            y = join(*layer(*split(x)))
+            if k == L - 1:  # only the batch rows of the final mean are read
+                keep = np.zeros(U + I, bool)
+                keep[rows] = True
+                y[~keep] = np.nan
+            if view is not None:
+                y = oracle.perturb(y, noise[view][k], eps)
+            acc = acc + y
+            x = y
+        finals.append(acc / L)
+    final, v1, v2 = finals
+    ue, pe, ne = final[u_idx], final[U + i_idx], final[U + j_idx]
+    rec, du, dp, dn = oracle.bpr_loss(ue, pe, ne)
+    l2, gl = oracle.l2_reg_loss(reg, ue, pe)
+    uu, ui = np.unique(u_idx), np.unique(i_idx)
+    lu, d1u, d2u = oracle.infonce(v1[uu], v2[uu], tau)
+    li, d1i, d2i = oracle.infonce(v1[U + ui], v2[U + ui], tau)
+    assert abs(rec - ref["rec"]) < 1e-12 and abs(l2 - ref["l2"]) < 1e-12 and abs(lam * (lu + li) - ref["cl"]) < 1e-10
+    # ---- backward: the three chains are the same linear map -> one merged Horner chain, seed = batch rows only ----
+    seed = np.zeros((U + I, d))
+    for idx, gg in ((u_idx, du + gl[0]), (U + i_idx, dp + gl[1]), (U + j_idx, dn), (uu, lam * (d1u + d2u)), (U + ui, lam * (d1i + d2i))):
+        np.add.at(seed, idx, gg / L)
+    acc = seed.copy()
+    for k in range(L - 1, 0, -1):
+        if k == L - 1:
+            assert not np.any(acc[np.setdiff1d(np.arange(U + I), rows)])  # the masked first product skips exactly zeros
+        acc = join(*layer(*split(acc))) + seed
+    grad = join(*layer(*split(acc)))
+    np.testing.assert_allclose(grad, ref["grad"], rtol=1e-9, atol=1e-13)
