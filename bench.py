@@ -838,8 +838,9 @@ def run_sharded(args, rank, world, local_rank):
         "config": {"workload": WORKLOAD,
                    "parallelism": f"bipartite-sharded x{world}: users dealt cyclically (u % world; their rows never leave the GPU), item tables replicated; per layer the "
                                   f"item-side SpMM epilogue stores partial rows into the slice owner's staging area (P2P, reduce-scatter), the owner sums, "
-                                  f"applies the epilogue and stores the finished rows to every rank ({route}); 2 device-side barriers per layer; batch losses "
-                                  "replicated on a compact [5B, d] table; one srb_shard_step call per step, captured in a CUDA graph",
+                                  f"applies the epilogue and stores the finished rows to every rank ({route}), beside the user-side product; 2 synchronisations per "
+                                  "layer folded into the kernels; last forward layer on the batch rows only; batch losses replicated on a compact [5B, d] "
+                                  "table; one srb_shard_step call per step, captured in a CUDA graph",
                    "l2": "no flush: per-step working set > 126 MB L2",
                    "inputs": f"{P} pre-sampled batches resident in HBM on every rank; CUDA-graph replay"},
         "clocks": clk,

@@ -231,7 +231,7 @@ struct LocalPlan {
   int64_t nce_ws_bytes;
 };
 
-static LocalPlan local_plan(int64_t U, int64_t I, int64_t Ug, int64_t d, int64_t B, int64_t hub_u, int64_t hub_t) {
+static LocalPlan local_plan(int64_t I, int64_t Ug, int64_t d, int64_t B, int64_t hub_u, int64_t hub_t) {
   LocalPlan p;
   int64_t off = 0;
   auto take = [&](int64_t bytes) {
@@ -638,7 +638,7 @@ static int make_ctx(const srb_shard_desc* s, void* stream, Ctx& c) {
   c.L = s->n_layers;
   c.B = s->batch_cap;
   c.sp = sym_plan(c.I, c.d, c.B, c.G);
-  c.lp = local_plan(c.U, c.I, c.Ug, c.d, c.B, s->Ru.hub.n_work, s->Rt.hub.n_work);
+  c.lp = local_plan(c.I, c.Ug, c.d, c.B, s->Ru.hub.n_work, s->Rt.hub.n_work);
   SRB_REQUIRE(s->sym_bytes >= c.sp.total, "shard: symmetric region too small (%lld < %lld)", (long long)s->sym_bytes, (long long)c.sp.total);
   SRB_REQUIRE(s->workspace && s->workspace_bytes >= c.lp.total, "shard: workspace too small (%lld < %lld)",
               (long long)s->workspace_bytes, (long long)c.lp.total);
@@ -655,7 +655,8 @@ extern "C" int srb_shard_plan(int32_t n_users, int32_t n_items, int32_t n_local_
   SRB_REQUIRE(out && world >= 1 && world <= 8 && n_items > 0 && d > 0 && batch_cap > 0 && hub_chunks_u >= 0 && hub_chunks_t >= 0,
               "shard_plan: bad arguments");
   const srb::SymPlan sp = srb::sym_plan(n_items, d, batch_cap, world);
-  const srb::LocalPlan lp = srb::local_plan(n_users, n_items, n_local_users, d, batch_cap, hub_chunks_u, hub_chunks_t);
+  (void)n_users;  // (the local workspace only depends on the rank's own user count)
+  const srb::LocalPlan lp = srb::local_plan(n_items, n_local_users, d, batch_cap, hub_chunks_u, hub_chunks_t);
   out->sym_bytes = sp.total;
   out->workspace_bytes = lp.total;
   out->item_params = sp.pi;
